@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- byte-mix embedding fwd+bwd throughput (tokens/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one forward + one backward of the fused byte-mix embedding over one
+synthetic batch (per GPU), plus -- for N > 1 -- the all-reduce(AVG) of the dense
+token / byte embedding gradients (the one exchange step of the path,
+spt/train_gpt.py:1320-1321, runs/7:697-700).  Prints ONE JSON line (rank 0).
+
+`value`   : tokens/s, whole job, inputs resident in HBM, CUDA-event timed.
+`e2e`     : same metric through the module API with token / byte ids in pinned host memory
+            (H2D every step) and a D2H read of the byte-embedding gradient every step.
+`roofline`: the dominant kernel (backward) timed with CUDA events recorded by the library
+            immediately around that kernel on its launch stream, against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port of the reference (eager torch CPU, all host cores) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mixture-of-tokenizers_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch
+
+V_TOK, V_BYTE = 50257, 458
+
+# name -> config.  N = tokens per GPU per step.
+WORKLOADS = {
+    # BASELINE.json configs[2]: modded-nanogpt 124M byte-mix embedding, 48K tokens/GPU/step, bf16.
+    # MoT-sum (runs/71:228-230,312-314) at model_dim 768 = 16 bytes x 48.
+    "mot-sum-124M-48k": dict(variant="V3", N=49152, Dt=768, bd=48, bpt=16, dtype="bf16"),
+    # what the reference runs ship (runs/71:496,500-501): 64K tokens, 1024 = 16 x 64
+    "mot-sum-medium-64k": dict(variant="V3", N=65536, Dt=1024, bd=64, bpt=16, dtype="bf16"),
+    "mot-sum-medium-48k": dict(variant="V3", N=49152, Dt=1024, bd=64, bpt=16, dtype="bf16"),
+    "mot-sum-1m": dict(variant="V3", N=1048576, Dt=1024, bd=64, bpt=16, dtype="bf16"),
+    "mot-concat-711": dict(variant="V4", N=65536, Dt=512, bd=32, bpt=16, dtype="bf16"),
+    "mot-norm-lambdas-71041": dict(variant="V3d", N=65536, Dt=1024, bd=64, bpt=16, dtype="bf16"),
+}
+DEFAULT_WORKLOAD = "mot-sum-124M-48k"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--tokens", type=int, default=0, help="override tokens per GPU per step")
+    ap.add_argument("--dist", choices=["uniform", "zipf"], default="uniform",
+                    help="token id distribution: uniform = the reference's own warm-up generator (runs/7:633-635)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.tokens:
+        w["N"] = args.tokens
+    w["name"] = args.workload
+    return w
+
+
+def algorithmic_bytes(w):
+    """BASELINE.md section 3 (ids given as a tensor, R = 1 because the mixed row is normalised)."""
+    e = 2 if w["dtype"] == "bf16" else 4
+    N, Dt, bd, bpt = w["N"], w["Dt"], w["bd"], w["bpt"]
+    Do = {"V3": Dt, "V3d": Dt, "V4": Dt + bpt * bd}[w["variant"]]
+    fwd = N * (4 + 4 * bpt + Dt * e + Do * e) + V_BYTE * bd * e
+    bwd = N * (Do * e + 4 + 4 * bpt + Dt * e) + V_TOK * Dt * e + V_BYTE * bd * e
+    return fwd, bwd, Do
+
+
+def make_tokens(N, dist, seed, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    if dist == "uniform":
+        return torch.randint(0, V_TOK - 1, (N,), generator=g, dtype=torch.int32).to(device)
+    # Zipf(1.0) over a seeded permutation of the vocabulary, EOT every ~800 tokens ("FineWeb-shape")
+    ranks = torch.arange(1, V_TOK, dtype=torch.float64)
+    p = (1.0 / ranks)
+    p /= p.sum()
+    perm = torch.randperm(V_TOK - 1, generator=g)
+    toks = perm[torch.multinomial(p, N, replacement=True, generator=g)].int()
+    eot = torch.rand(N, generator=g) < 1.0 / 800
+    toks[eot] = V_TOK - 1
+    return toks.to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, eager torch on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(w, n_sample, seed=12345):
+    from oracle import mot_oracle as O
+    spec = O.VARIANTS[w["variant"]][0]
+    g = torch.Generator().manual_seed(seed)
+    Dt, bd, bpt = w["Dt"], w["bd"], w["bpt"]
+    Do = algorithmic_bytes(w)[2]
+    dt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
+    toks = torch.randint(0, V_TOK - 1, (n_sample,), generator=g, dtype=torch.int32)
+    slot_major = w["variant"].startswith("V3")
+    ids = torch.randint(0, V_BYTE, (bpt, n_sample) if slot_major else (1, n_sample * bpt), generator=g, dtype=torch.int32)
+    E_tok = torch.randn(V_TOK, Dt, generator=g).to(dt)   # nn.Embedding N(0,1) -> bf16 (train_gpt.py:1124-1126)
+    E_byte = torch.randn(V_BYTE, bd, generator=g).to(dt)
+    gout = torch.randn(n_sample, Do, generator=g).to(dt)
+    kw = dict(bpt=bpt, slot_major=slot_major)
+    if w["variant"] in ("V3c", "V3d"):
+        kw["lam_tok"], kw["lam_byte"] = torch.tensor(0.5), torch.tensor(0.5)
+
+    def step():
+        # the reference computes in the parameter dtype (eager bf16); math_dtype=dt reproduces that cost
+        O.mot_embed_fwd_bwd(spec, toks, ids, E_tok, E_byte, gout, math_dtype=dt, **kw)
+    return step
+
+
+def time_cpu_reference(w, steps, warmup, budget_s=20.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_sample = min(w["N"], 8192)
+    step = cpu_reference_step_fn(w, n_sample)
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
+    reps = max(1, min(steps, int(budget_s / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n_sample / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} steps of {n_sample} tokens of the same workload (oracle/mot_oracle.py, eager torch "
+                      f"{w['dtype']} on CPU, fwd+bwd incl. dense [50257,{w['Dt']}] grad)",
+            "ms_per_step": dt * 1e3, "n_sample": n_sample, "steps": reps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload_config(args)
+    r = time_cpu_reference(w, args.steps, args.warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": r["value"], "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["name"], "variant": w["variant"], "tokens_per_step": r["n_sample"],
+                       "token_dim": w["Dt"], "byte_dim": w["bd"], "bytes_per_token": w["bpt"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import mot_b200
+    from mot_b200 import ops, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    w = workload_config(args)
+    N, Dt, bd, bpt = w["N"], w["Dt"], w["bd"], w["bpt"]
+    dt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
+    esz = 2 if dt == torch.bfloat16 else 4
+    A_fwd, A_bwd, Do = algorithmic_bytes(w)
+    spec_kw = dict(mot_b200.RUN_VARIANTS[w["variant"]])
+    slot_major = spec_kw.get("slot_major", False)
+    spec = mot_b200.MixSpec(**spec_kw)
+
+    # ---- synthetic inputs, resident in HBM (rank r owns its own shard of the stream: seed + rank) ----
+    g = torch.Generator(device=dev).manual_seed(12345)       # tables identical on every rank (replicas)
+    E_tok = torch.randn(V_TOK, Dt, generator=g, device=dev).to(dt)
+    E_byte = torch.randn(V_BYTE, bd, generator=g, device=dev).to(dt)
+    gd = torch.Generator(device=dev).manual_seed(12345 + 1000 * (rank + 1))
+    tok_host = make_tokens(N, args.dist, 12345 + rank).pin_memory()
+    tok = tok_host.to(dev)
+    ids_shape = (bpt, N) if slot_major else (1, N * bpt)
+    ids = torch.randint(0, V_BYTE, ids_shape, generator=gd, device=dev, dtype=torch.int32)  # runs/7:635
+    ids_host = ids.cpu().pin_memory()
+    gout = torch.randn(N, Do, generator=gd, device=dev).to(dt)
+    lam = torch.tensor([0.5, 0.5], device=dev) if w["variant"] in ("V3c", "V3d") else None
+    out = torch.empty(N, Do, dtype=dt, device=dev)
+    # one flat gradient bucket [gE_tok | gE_byte] -> a single NCCL all-reduce
+    n_tok_g, n_byte_g = V_TOK * Dt, V_BYTE * bd
+    flat = torch.empty(n_tok_g + n_byte_g, dtype=dt, device=dev)
+    gE_tok, gE_byte = flat[:n_tok_g].view(V_TOK, Dt), flat[n_tok_g:].view(V_BYTE, bd)
+    g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
+    desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
+    ws = torch.empty(ops.embed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
+
+    def step():
+        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
+        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.lib()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed, clocks sampled meanwhile ----
+    K = args.steps
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in fwd_ev + bwd_ev:  # materialise the cudaEvent_t handles
+        a.record(); b.record()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    mot_b200.reset_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        lib.mot_profile_events(fwd_ev[i][0].cuda_event, fwd_ev[i][1].cuda_event, bwd_ev[i][0].cuda_event, bwd_ev[i][1].cuda_event)
+        step()
+    e1.record()
+    barrier()
+    lib.mot_profile_events(None, None, None, None)
+    launches = mot_b200.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = world * N / (ms_step * 1e-3)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / K
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / K
+
+    # ---- e2e: module API, ids in pinned host memory, H2D every step, D2H of the byte-table gradient ----
+    e2e = None
+    if not args.no_e2e:
+        mod = mot_b200.MoTEmbedding(V_TOK, V_BYTE, Dt, bd, bpt, variant=w["variant"]).to(dev).to(dt)
+        with torch.no_grad():
+            mod.embed_tokens.weight.copy_(E_tok); mod.embed_bytes.weight.copy_(E_byte)
+        res_host = torch.empty(V_BYTE, bd, dtype=dt).pin_memory()
+
+        def e2e_step():
+            for p_ in mod.parameters():
+                p_.grad = None
+            t_in = tok_host.to(dev, non_blocking=True)
+            b_in = ids_host.to(dev, non_blocking=True)
+            x = mod(t_in, b_in)
+            x.backward(gout.view_as(x))
+            if world > 1:
+                for p_ in mod.parameters():
+                    dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+            res_host.copy_(mod.embed_bytes.weight.grad, non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the caller reads the result on the host every step
+
+        for _ in range(max(3, args.warmup // 4)):
+            e2e_step()
+        barrier()
+        Ke = max(10, K // 4)
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        barrier()
+        t_e = torch.tensor([(time.perf_counter() - t0) / Ke], device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N / float(t_e.item()), "unit": "tokens/s",
+               "h2d_bytes_per_step": tok_host.numel() * 4 + ids_host.numel() * 4,
+               "d2h_bytes_per_step": res_host.numel() * esz, "ms_per_step": float(t_e.item()) * 1e3,
+               "api": "mot_b200.MoTEmbedding.forward + autograd backward", "steps": Ke}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        dom_bytes, dom_ms, dom = (A_bwd, bwd_ms, "mot_bwd_kernel") if bwd_ms >= fwd_ms else (A_fwd, fwd_ms, "mot_fwd_kernel")
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["name"], "variant": w["variant"], "tokens_per_gpu_per_step": N, "token_dim": Dt,
+                       "byte_dim": bd, "bytes_per_token": bpt, "out_dim": Do, "token_dist": args.dist,
+                       "byte_ids": "uniform randint(0,458), given as a tensor (runs/7:635 layout)",
+                       "l2": f"working set {(2 * V_TOK * Dt * esz + 2 * N * Do * esz) / 1e6:.0f} MB > 126 MB L2, no flush",
+                       "parallelism": f"dp{world}" + (", one flat-bucket NCCL all-reduce(AVG) per step" if world > 1 else "")},
+            "tokens_per_sec_per_gpu": value / world,
+            "kernel_ms": {"fwd": fwd_ms, "bwd_main": bwd_ms},
+            "step_hbm_gbs": (A_fwd + A_bwd) / (ms_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0, "traffic": None,
+                         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms, "peak_source": peak_src,
+                         "fwd": {"achieved": A_fwd / (fwd_ms * 1e-3) / 1e9, "bytes": A_fwd, "ms": fwd_ms},
+                         "bwd": {"achieved": A_bwd / (bwd_ms * 1e-3) / 1e9, "bytes": A_bwd, "ms": bwd_ms}},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_cpu_reference(w, steps=50, warmup=2, budget_s=15.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,140 @@
+/*
+ * mot_b200.h -- C ABI of the B200-native byte-mix embedding path of
+ * mixture-of-tokenizers (libmot_b200.so, sm_100a only).
+ *
+ * The reference has no FFI: the path is inline PyTorch module code.  Each entry
+ * point below names the reference lines whose work it replaces (paths relative
+ * to the reference checkout; "spt" = scaled-pre-train, "runs/N" =
+ * modded-nanogpt/runs/N_mot-in_toks-valemb.py).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing is allocated
+ *     or freed by the library; outputs, gradients and workspace are caller-provided;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
+ *     host synchronisation, no host reads of device data (CUDA-graph capturable);
+ *   - return value: 0 = MOT_OK, otherwise an error code for mot_strerror();
+ *   - token ids are int32; byte ids are int32 or int64 (MOT_F_IDS_I64);
+ *   - tables, outputs and dense gradients share one element type (MotDesc.dtype);
+ *   - tok_dim, byte_dim and out_dim must be multiples of 8 elements and all table /
+ *     output pointers 16-byte aligned (128-bit accesses).
+ */
+#ifndef MOT_B200_H
+#define MOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOT_B200_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+enum {
+  MOT_OK = 0,
+  MOT_ERR_BAD_ARG = 1,     /* null pointer / non-positive size / inconsistent dims   */
+  MOT_ERR_UNSUPPORTED = 2, /* a reference option this library refuses (no fallback)  */
+  MOT_ERR_MISALIGNED = 3,  /* pointer not 16-byte aligned / dim not a multiple of 8  */
+  MOT_ERR_WORKSPACE = 4,   /* workspace smaller than mot_embed_workspace_bytes()     */
+  MOT_ERR_CUDA = 5,        /* launch failed; see mot_last_cuda_error()               */
+  MOT_ERR_NO_DEVICE = 6    /* no sm_100 device is current                            */
+};
+
+/* ---- element / id types ------------------------------------------------ */
+enum { MOT_BF16 = 0, MOT_F32 = 1 };
+/* storage of the ttb table: int16 (native), or the reference's float containers:
+ * fp32 nn.Embedding (spt/data_creation.py:51-58) and the bf16-cast table of the
+ * runs (runs/7:441) whose ids > 256 are rounded -- read back with truncation like
+ * `.to(int64)` (spt/data_creation.py:63). */
+enum { MOT_TTB_I16 = 0, MOT_TTB_F32 = 1, MOT_TTB_BF16 = 2 };
+
+/* ---- how token and byte rows are combined -------------- */
+enum {
+  MOT_ADD = 0,        /* z = u + concat_k(w_k)        tok_dim == bpt*byte_dim == out_dim (runs/71:228-230) */
+  MOT_CONCAT = 1,     /* z = [u | concat_k(w_k)]      out_dim == tok_dim + bpt*byte_dim  (runs/711:224-232,
+                         the A operand of the projection variants runs/7:226-234, spt/train_gpt.py:439-443) */
+  MOT_TOK_ONLY = 2,   /* z = u                        (spt/train_gpt.py:342-348)          */
+  MOT_BYTES_ONLY = 3, /* z = concat_k(w_k)            (runs/4_bytes-in_toks-valemb.py:313) */
+  MOT_MEAN = 4        /* z = u + mean_k(w_k)          byte_dim == tok_dim (inference/inference.py:267) */
+};
+
+enum {
+  MOT_F_TOK_NORM = 1 << 0,     /* u = lam_tok * rms_norm(E_tok[tok])          (runs/7:317)            */
+  MOT_F_BYTE_NORM = 1 << 1,    /* w_k = lam_byte * rms_norm(E_byte[id_k])     (runs/7:318, over byte_dim) */
+  MOT_F_OUT_NORM = 1 << 2,     /* out = rms_norm(z)                           (runs/71:230)           */
+  MOT_F_BYTES_FIRST = 1 << 3,  /* MOT_CONCAT order [bytes | tok]              (mathblations/model.py:267) */
+  MOT_F_SLOT_MAJOR = 1 << 4,   /* byte ids are [bpt, n_tokens] (runs/71:479 `.view(16,-1)`), else [n_tokens, bpt] */
+  MOT_F_IDS_FROM_TTB = 1 << 5, /* no byte-id tensor: ids are read from the ttb table inside the kernel */
+  MOT_F_TTB_SCRAMBLE = 1 << 6, /* with IDS_FROM_TTB: slot i of position s is flat byte i*seq_len + s of its
+                                  row of seq_len tokens (the `.view(bpt,-1)` of runs/71:479)           */
+  MOT_F_IDS_I64 = 1 << 7,      /* byte-id tensors hold int64 (spt), else int32 (runs)                  */
+  MOT_F_HAS_LAMBDAS = 1 << 8   /* lam[0] = lam_tok, lam[1] = lam_byte (runs/74:314-315)                */
+};
+
+typedef struct MotDesc {
+  int32_t abi_version; /* MOT_B200_ABI_VERSION */
+  int32_t dtype;       /* MOT_BF16 | MOT_F32 */
+  int64_t n_tokens;    /* positions in this call (B*S) */
+  int64_t seq_len;     /* tokens per row (only used by MOT_F_TTB_SCRAMBLE; n_tokens % seq_len == 0) */
+  int32_t tok_vocab;   /* rows of E_tok  (50257) */
+  int32_t byte_vocab;  /* rows of E_byte (458; 14 for mathblations digits) */
+  int32_t bpt;         /* bytes (digits) per token, 1..32 */
+  int32_t tok_dim;
+  int32_t byte_dim;
+  int32_t out_dim;
+  int32_t combine;     /* MOT_ADD ... */
+  int32_t flags;       /* MOT_F_* */
+  int32_t ttb_dtype;   /* MOT_TTB_* (only with MOT_F_IDS_FROM_TTB) */
+  float eps;           /* rms_norm eps; the reference uses torch's default, finfo(float32).eps */
+} MotDesc;
+
+const char* mot_strerror(int rc);
+int mot_abi_version(void);
+/* cudaGetErrorString of the last failed launch on this thread ("" if none). */
+const char* mot_last_cuda_error(void);
+/* Number of kernels this library launched since load / since the last reset (process-wide). */
+int64_t mot_launch_count(void);
+void mot_launch_count_reset(void);
+/* Measurement hook (bench.py): cudaEvent_t pairs recorded on the launch stream immediately around the
+ * main forward kernel and the main backward kernel of the following calls; NULL disables a pair. */
+void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* bwd_stop);
+
+/* tokens -> padded byte ids.
+ * Replaces tokens_to_bytes (spt/data_creation.py:61-67, runs/7:444-450): gather ttb rows
+ * and cast to integer.  out is [n, bpt] token-major, int64 when out_i64 != 0 else int32. */
+int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
+                   int32_t ttb_dtype, void* out, int32_t out_i64, void* stream);
+
+/* Workspace needed by mot_embed_bwd for this descriptor (bytes, 256-aligned). */
+size_t mot_embed_workspace_bytes(const MotDesc* d);
+
+/* Fused forward: out[n_tokens, out_dim] =
+ *   f_out( combine( lam_tok * f_tok(E_tok[tok]),  lam_byte * f_byte(E_byte[byte ids]) ) ).
+ * Replaces the embedding + mixin lines of GPT.forward (runs/71:312-314 + mixin_bytes :228-230 and
+ * every variant of SURVEY.md 2.4 without a dense projection; spt/train_gpt.py:342-379).  For the
+ * projection variants it produces the A operand [tok | bytes] that mot_linear_* consumes.
+ *   byte_ids : int32/int64, NULL with MOT_F_IDS_FROM_TTB (then `ttb` is used), ignored for TOK_ONLY
+ *   lam      : device float[2] or NULL (== {1,1}) */
+int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                  const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream);
+
+/* Sort plan for the backward (token ids only; reusable by every table gathered with `tok`). */
+int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, void* stream);
+
+/* Fused backward: the autograd graph of the lines above (rms_norm bwd, split, and the two
+ * embedding_dense_backward scatter-adds).  gE_tok [tok_vocab, tok_dim] and gE_byte
+ * [byte_vocab, byte_dim] are DENSE and fully overwritten (rows never gathered get zeros), so a
+ * caller can all-reduce / feed them to the optimizer exactly like the reference's param.grad.
+ *   g_lam : device float[2], overwritten (d lam_tok, d lam_byte), or NULL
+ *   plan_ready != 0 : `workspace` already holds mot_embed_plan() for these tokens */
+int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                  const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                  void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
+                  int32_t plan_ready, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOT_B200_H */

@@ -1,0 +1,140 @@
+// Shared device/host helpers for libmot_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mot_b200.h"
+
+namespace mot {
+
+constexpr int kWarp = 32;
+constexpr int kChunk = 8;  // elements handled by one lane per chunk (16 B of bf16 / 32 B of fp32)
+
+// ---------------------------------------------------------------- host side
+extern thread_local cudaError_t g_last_cuda_error;
+void count_launch(int n = 1);
+int check_launch();  // cudaGetLastError -> MOT_OK / MOT_ERR_CUDA
+int device_props(int* sm_count, int* smem_optin);
+// optional event pairs recorded around the main forward / backward kernel (mot_profile_events)
+extern cudaEvent_t g_prof_fwd_start, g_prof_fwd_stop, g_prof_start, g_prof_stop;
+
+// ---------------------------------------------------------------- device side
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_16(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+
+__device__ __forceinline__ void bf16x2_to_f32(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 8 consecutive elements <-> 8 floats.  Pointers must be 16-byte aligned.  `Raw` is the
+// register image of the 8 elements as loaded (kept packed while a load is in flight).
+template <typename T>
+struct Vec8;
+
+template <>
+struct Vec8<__nv_bfloat16> {
+  using Raw = uint4;
+  __device__ __forceinline__ static Raw ldg_raw(const __nv_bfloat16* p) { return ldg_nc_16(p); }
+  __device__ __forceinline__ static Raw lds_raw(const __nv_bfloat16* p) { return lds_16(p); }
+  __device__ __forceinline__ static Raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[8]) {
+    bf16x2_to_f32(r.x, v[0], v[1]);
+    bf16x2_to_f32(r.y, v[2], v[3]);
+    bf16x2_to_f32(r.z, v[4], v[5]);
+    bf16x2_to_f32(r.w, v[6], v[7]);
+  }
+  __device__ __forceinline__ static void stg(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    r.x = f32x2_to_bf16x2(v[0], v[1]);
+    r.y = f32x2_to_bf16x2(v[2], v[3]);
+    r.z = f32x2_to_bf16x2(v[4], v[5]);
+    r.w = f32x2_to_bf16x2(v[6], v[7]);
+    stg_16(p, r);
+  }
+};
+
+template <>
+struct Vec8<float> {
+  struct Raw {
+    uint4 a, b;
+  };
+  __device__ __forceinline__ static Raw ldg_raw(const float* p) { return Raw{ldg_nc_16(p), ldg_nc_16(p + 4)}; }
+  __device__ __forceinline__ static Raw lds_raw(const float* p) { return Raw{lds_16(p), lds_16(p + 4)}; }
+  __device__ __forceinline__ static Raw zero_raw() { return Raw{make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}; }
+  __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  }
+  __device__ __forceinline__ static void stg(float* p, const float (&v)[8]) {
+    uint4 a, b;
+    a.x = __float_as_uint(v[0]); a.y = __float_as_uint(v[1]); a.z = __float_as_uint(v[2]); a.w = __float_as_uint(v[3]);
+    b.x = __float_as_uint(v[4]); b.y = __float_as_uint(v[5]); b.z = __float_as_uint(v[6]); b.w = __float_as_uint(v[7]);
+    stg_16(p, a);
+    stg_16(p + 4, b);
+  }
+};
+
+// ---- mbarrier + 1-D bulk (TMA) copy global -> shared, used to stage the byte table ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bytes must be a multiple of 16, both pointers 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace mot

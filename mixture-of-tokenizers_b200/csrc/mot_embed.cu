@@ -1,0 +1,323 @@
+// Host side of the fused byte-mix embedding: validation, workspace layout, plan, C ABI.
+#include "mot_embed_kernels.cuh"
+
+namespace mot {
+
+// ======================================================================================
+// Backward plan: group positions by token id (counting sort over the vocabulary)
+// ======================================================================================
+__global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, int V, int* __restrict__ cnt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
+}
+
+// single CTA, 1024 threads: four exclusive scans over the vocabulary in one pass
+__global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
+  __shared__ int4 wsum[32];
+  __shared__ int4 carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (p.V + 1023) / 1024;
+  const int v0 = tid * per, v1 = min(v0 + per, p.V);
+  int4 loc = make_int4(0, 0, 0, 0);
+  for (int v = v0; v < v1; ++v) {
+    const int c = p.cnt[v];
+    const int nch = (c + p.L - 1) / p.L;
+    loc.x += c;
+    loc.y += nch;
+    loc.z += (nch > 1);
+    loc.w += (nch > 1) ? nch : 0;
+  }
+  int4 inc = loc;  // inclusive scan over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int4 t;
+    t.x = __shfl_up_sync(0xffffffffu, inc.x, o);
+    t.y = __shfl_up_sync(0xffffffffu, inc.y, o);
+    t.z = __shfl_up_sync(0xffffffffu, inc.z, o);
+    t.w = __shfl_up_sync(0xffffffffu, inc.w, o);
+    if (lane >= o) { inc.x += t.x; inc.y += t.y; inc.z += t.z; inc.w += t.w; }
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int4 w = wsum[lane];
+    int4 wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int4 t;
+      t.x = __shfl_up_sync(0xffffffffu, wi.x, o);
+      t.y = __shfl_up_sync(0xffffffffu, wi.y, o);
+      t.z = __shfl_up_sync(0xffffffffu, wi.z, o);
+      t.w = __shfl_up_sync(0xffffffffu, wi.w, o);
+      if (lane >= o) { wi.x += t.x; wi.y += t.y; wi.z += t.z; wi.w += t.w; }
+    }
+    wsum[lane] = make_int4(wi.x - w.x, wi.y - w.y, wi.z - w.z, wi.w - w.w);  // exclusive warp offsets
+    if (lane == 31) carry_s = wi;                                            // totals
+  }
+  __syncthreads();
+  const int4 wo = wsum[warp];
+  int4 run = make_int4(wo.x + inc.x - loc.x, wo.y + inc.y - loc.y, wo.z + inc.z - loc.z, wo.w + inc.w - loc.w);
+  for (int v = v0; v < v1; ++v) {
+    const int c = p.cnt[v];
+    const int nch = (c + p.L - 1) / p.L;
+    p.off[v] = run.x;
+    p.item_off[v] = run.y;
+    p.hot_off[v] = run.z;
+    p.pslot_off[v] = run.w;
+    run.x += c;
+    run.y += nch;
+    run.z += (nch > 1);
+    run.w += (nch > 1) ? nch : 0;
+  }
+  if (tid == 0) {
+    const int4 tot = carry_s;
+    p.off[p.V] = tot.x;
+    p.item_off[p.V] = tot.y;
+    p.hot_off[p.V] = tot.z;
+    p.pslot_off[p.V] = tot.w;
+  }
+}
+
+// threads [0, N): scatter positions into their token's segment (cursor = cnt, counted back down to 0);
+// threads [0, V): emit the work items of token v.
+__global__ void plan_fill_kernel(EmbedParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.N) {
+    const int v = clampi(p.tok[i], p.V - 1);
+    const int slot = atomicSub(&p.cnt[v], 1) - 1;
+    p.order[p.off[v] + slot] = (int)i;
+  }
+  if (i < p.V) {
+    const int v = (int)i;
+    const int start = p.off[v], c = p.off[v + 1] - start;
+    const int nch = (c + p.L - 1) / p.L;
+    const int ib = p.item_off[v];
+    const int ps = p.pslot_off[v];
+    for (int j = 0; j < nch; ++j)
+      p.items[ib + j] = make_int4(v, start + j * p.L, min(p.L, c - j * p.L), nch > 1 ? ps + j : -1);
+    if (nch > 1) p.hot_rows[p.hot_off[v]] = make_int4(v, ps, nch, 0);
+  }
+}
+
+
+__global__ void mot_lam_store_kernel(const float* __restrict__ acc, float* __restrict__ g_lam) {
+  if (threadIdx.x < 2) g_lam[threadIdx.x] = acc[threadIdx.x];
+}
+
+// ======================================================================================
+// Host side
+// ======================================================================================
+static int validate(const MotDesc* d) {
+  if (!d) return MOT_ERR_BAD_ARG;
+  if (d->abi_version != MOT_B200_ABI_VERSION) return MOT_ERR_BAD_ARG;
+  if (d->dtype != MOT_BF16 && d->dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
+  if (d->n_tokens < 0 || d->n_tokens > 0x7fffffffLL) return MOT_ERR_BAD_ARG;
+  if (d->combine < MOT_ADD || d->combine > MOT_MEAN) return MOT_ERR_UNSUPPORTED;
+  const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
+  if (d->out_dim <= 0 || d->out_dim % 8) return MOT_ERR_MISALIGNED;
+  if (has_tok && (d->tok_vocab <= 0 || d->tok_dim <= 0)) return MOT_ERR_BAD_ARG;
+  if (has_tok && d->tok_dim % 8) return MOT_ERR_MISALIGNED;
+  if (has_bytes) {
+    if (d->byte_vocab <= 0 || d->byte_dim <= 0 || d->bpt <= 0 || d->bpt > 32) return MOT_ERR_BAD_ARG;
+    if (d->byte_dim % 8) return MOT_ERR_MISALIGNED;
+  }
+  const long long db = (long long)d->bpt * d->byte_dim;
+  switch (d->combine) {
+    case MOT_ADD: if (d->tok_dim != db || d->out_dim != d->tok_dim) return MOT_ERR_BAD_ARG; break;
+    case MOT_CONCAT: if (d->out_dim != d->tok_dim + db) return MOT_ERR_BAD_ARG; break;
+    case MOT_TOK_ONLY: if (d->out_dim != d->tok_dim) return MOT_ERR_BAD_ARG; break;
+    case MOT_BYTES_ONLY: if (d->out_dim != db) return MOT_ERR_BAD_ARG; break;
+    case MOT_MEAN: if (d->byte_dim != d->tok_dim || d->out_dim != d->tok_dim) return MOT_ERR_BAD_ARG; break;
+  }
+  if (d->out_dim > 8 * 32 * 8) return MOT_ERR_UNSUPPORTED;  // CPL <= 8
+  if ((d->flags & MOT_F_IDS_FROM_TTB) && has_bytes) {
+    if (d->ttb_dtype < MOT_TTB_I16 || d->ttb_dtype > MOT_TTB_BF16) return MOT_ERR_UNSUPPORTED;
+    if (d->flags & MOT_F_TTB_SCRAMBLE)
+      if (d->seq_len <= 0 || d->n_tokens % d->seq_len) return MOT_ERR_BAD_ARG;
+  }
+  return MOT_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static void fill_params(const MotDesc* d, EmbedParams& p) {
+  p = EmbedParams{};
+  p.N = d->n_tokens;
+  p.T = d->seq_len > 0 ? d->seq_len : (d->n_tokens > 0 ? d->n_tokens : 1);
+  p.V = d->tok_vocab;
+  p.Vb = d->combine == MOT_TOK_ONLY ? 0 : d->byte_vocab;
+  p.bpt = d->combine == MOT_TOK_ONLY ? 0 : d->bpt;
+  p.Dt = d->combine == MOT_BYTES_ONLY ? 0 : d->tok_dim;
+  p.bd = d->combine == MOT_TOK_ONLY ? 8 : d->byte_dim;
+  p.Do = d->out_dim;
+  p.combine = d->combine;
+  p.flags = d->flags;
+  p.ttb_dtype = d->ttb_dtype;
+  p.n_chunks = d->out_dim / kChunk;
+  p.eps = d->eps;
+  // occurrences per work item: large enough that hot-row partials stay a few MB, small enough that one
+  // item is a short tail
+  long long L = 16;
+  while (L < 256 && d->n_tokens / L > 4096) L <<= 1;
+  p.L = (int)L;
+}
+
+struct WsLayout {
+  size_t cnt, off, item_off, hot_off, pslot_off, order, items, hot_rows, partial, byte_acc, lam_acc, total;
+  long long max_items, max_hot, max_pslots;
+};
+
+static WsLayout ws_layout(const EmbedParams& p) {
+  WsLayout w{};
+  const long long V = p.V > 0 ? p.V : 1, N = p.N > 0 ? p.N : 1;
+  const long long chunks = N / p.L + 1;
+  w.max_hot = chunks < V ? chunks : V;
+  w.max_pslots = chunks + w.max_hot;
+  w.max_items = (N < V ? N : V) + chunks;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  // zeroed region first: cnt | byte_acc | lam_acc (one memset)
+  w.cnt = take((size_t)V * 4);
+  w.byte_acc = take((size_t)(p.Vb > 0 ? p.Vb : 1) * p.bd * 4);
+  w.lam_acc = take(16);
+  w.off = take((size_t)(V + 1) * 4);
+  w.item_off = take((size_t)(V + 1) * 4);
+  w.hot_off = take((size_t)(V + 1) * 4);
+  w.pslot_off = take((size_t)(V + 1) * 4);
+  w.order = take((size_t)N * 4);
+  w.items = take((size_t)w.max_items * 16);
+  w.hot_rows = take((size_t)w.max_hot * 16);
+  w.partial = take((size_t)w.max_pslots * (p.Dt > 0 ? p.Dt : 8) * 4);
+  w.total = o;
+  return w;
+}
+
+static void bind_ws(EmbedParams& p, const WsLayout& w, void* ws) {
+  char* b = reinterpret_cast<char*>(ws);
+  p.cnt = reinterpret_cast<int*>(b + w.cnt);
+  p.byte_acc = reinterpret_cast<float*>(b + w.byte_acc);
+  p.lam_acc = reinterpret_cast<float*>(b + w.lam_acc);
+  p.off = reinterpret_cast<int*>(b + w.off);
+  p.item_off = reinterpret_cast<int*>(b + w.item_off);
+  p.hot_off = reinterpret_cast<int*>(b + w.hot_off);
+  p.pslot_off = reinterpret_cast<int*>(b + w.pslot_off);
+  p.order = reinterpret_cast<int*>(b + w.order);
+  p.items = reinterpret_cast<int4*>(b + w.items);
+  p.hot_rows = reinterpret_cast<int4*>(b + w.hot_rows);
+  p.partial = reinterpret_cast<float*>(b + w.partial);
+}
+
+static int run_plan(const EmbedParams& p, cudaStream_t s) {
+  if (p.combine == MOT_BYTES_ONLY || p.N == 0) return MOT_OK;
+  long long hb = (p.N + 255) / 256;
+  if (hb > 2048) hb = 2048;
+  plan_hist_kernel<<<(unsigned)hb, 256, 0, s>>>(p.tok, p.N, p.V, p.cnt);
+  plan_scan_kernel<<<1, 1024, 0, s>>>(p);
+  const long long m = p.N > p.V ? p.N : p.V;
+  plan_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(p);
+  count_launch(3);
+  return check_launch();
+}
+
+}  // namespace mot
+
+using namespace mot;
+
+extern "C" size_t mot_embed_workspace_bytes(const MotDesc* d) {
+  if (validate(d) != MOT_OK) return 0;
+  EmbedParams p;
+  fill_params(d, p);
+  return ws_layout(p).total;
+}
+
+extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                             const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream) {
+  if (int rc = validate(d)) return rc;
+  const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
+  if (!out || (has_tok && (!tok || !E_tok)) || (has_bytes && !E_byte)) return MOT_ERR_BAD_ARG;
+  if (has_bytes) {
+    if (d->flags & MOT_F_IDS_FROM_TTB) { if (!ttb || !tok) return MOT_ERR_BAD_ARG; }
+    else if (!byte_ids) return MOT_ERR_BAD_ARG;
+  }
+  if ((d->flags & MOT_F_HAS_LAMBDAS) && !lam) return MOT_ERR_BAD_ARG;
+  if (!aligned16(out) || !aligned16(E_tok) || !aligned16(E_byte)) return MOT_ERR_MISALIGNED;
+  if (d->n_tokens == 0) return MOT_OK;
+  EmbedParams p;
+  fill_params(d, p);
+  p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam; p.out = out;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == MOT_BF16 ? dispatch_fwd_bf16(p, s) : dispatch_fwd_f32(p, s);
+}
+
+extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, void* stream) {
+  if (int rc = validate(d)) return rc;
+  if (!workspace) return MOT_ERR_BAD_ARG;
+  if (d->combine != MOT_BYTES_ONLY && !tok) return MOT_ERR_BAD_ARG;
+  EmbedParams p;
+  fill_params(d, p);
+  const WsLayout w = ws_layout(p);
+  if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
+  if (!aligned16(workspace)) return MOT_ERR_MISALIGNED;
+  bind_ws(p, w, workspace);
+  p.tok = tok;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // zero cnt | byte_acc | lam_acc (contiguous at the head of the workspace)
+  if (cudaMemsetAsync(workspace, 0, w.off, s) != cudaSuccess) return check_launch();
+  return run_plan(p, s);
+}
+
+extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                             const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                             void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
+                             int32_t plan_ready, void* stream) {
+  if (int rc = validate(d)) return rc;
+  const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
+  if (!grad_out || !workspace) return MOT_ERR_BAD_ARG;
+  if (has_tok && (!tok || !E_tok || !gE_tok)) return MOT_ERR_BAD_ARG;
+  if (has_bytes && (!E_byte || !gE_byte)) return MOT_ERR_BAD_ARG;
+  if (has_bytes) {
+    if (d->flags & MOT_F_IDS_FROM_TTB) { if (!ttb || !tok) return MOT_ERR_BAD_ARG; }
+    else if (!byte_ids) return MOT_ERR_BAD_ARG;
+  }
+  if ((d->flags & MOT_F_HAS_LAMBDAS) && (!lam || !g_lam)) return MOT_ERR_BAD_ARG;
+  if (!aligned16(grad_out) || !aligned16(E_tok) || !aligned16(E_byte) || !aligned16(gE_tok) || !aligned16(gE_byte) ||
+      !aligned16(workspace))
+    return MOT_ERR_MISALIGNED;
+  EmbedParams p;
+  fill_params(d, p);
+  const WsLayout w = ws_layout(p);
+  if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
+  bind_ws(p, w, workspace);
+  p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam;
+  p.gout = grad_out; p.gE_tok = gE_tok; p.gE_byte = gE_byte; p.g_lam = g_lam;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
+  if (d->n_tokens == 0) {  // nothing gathered: dense zero grads
+    if (has_tok && cudaMemsetAsync(gE_tok, 0, (size_t)d->tok_vocab * d->tok_dim * esz, s) != cudaSuccess) return check_launch();
+    if (has_bytes && cudaMemsetAsync(gE_byte, 0, (size_t)d->byte_vocab * d->byte_dim * esz, s) != cudaSuccess) return check_launch();
+    if (g_lam && cudaMemsetAsync(g_lam, 0, 8, s) != cudaSuccess) return check_launch();
+    return MOT_OK;
+  }
+  if (!plan_ready) {
+    if (cudaMemsetAsync(workspace, 0, w.off, s) != cudaSuccess) return check_launch();
+    if (int rc = run_plan(p, s)) return rc;
+  } else {  // plan kept from mot_embed_plan(): only the accumulators need clearing
+    if (cudaMemsetAsync(reinterpret_cast<char*>(workspace) + w.byte_acc, 0, w.off - w.byte_acc, s) != cudaSuccess)
+      return check_launch();
+  }
+  int rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
+  if (rc) return rc;
+  int sms = 0, optin = 0;
+  device_props(&sms, &optin);
+  rc = d->dtype == MOT_BF16 ? launch_finalize_bf16(p, sms, s) : launch_finalize_f32(p, sms, s);
+  if (rc) return rc;
+  if ((d->flags & MOT_F_HAS_LAMBDAS) && g_lam) {
+    mot_lam_store_kernel<<<1, 32, 0, s>>>(p.lam_acc, g_lam);
+    count_launch();
+  }
+  return check_launch();
+}

@@ -1,0 +1,12 @@
+// Backward kernel instantiations (row widths 1025..2048 elements), element type __nv_bfloat16.
+#include "mot_embed_kernels.cuh"
+namespace mot {
+int dispatch_bwd_wide_bf16(const EmbedParams& p, cudaStream_t s) {
+  using T = __nv_bfloat16;
+  switch ((p.n_chunks + 31) / 32) {
+    case 5: case 6: return launch_bwd<T, 6>(p, s);
+    case 7: case 8: return launch_bwd<T, 8>(p, s);
+  }
+  return MOT_ERR_UNSUPPORTED;
+}
+}  // namespace mot

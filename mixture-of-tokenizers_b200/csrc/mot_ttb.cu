@@ -1,0 +1,76 @@
+// Integer half of the path: token ids -> padded byte ids.
+//
+// Replaces tokens_to_bytes (spt/data_creation.py:61-67; runs/7:444-450): `emb(tokens).to(int64)`
+// on a float nn.Embedding that holds the ttb table.  Here the table is int16 [V, bpt] (or the
+// reference's fp32 / bf16 containers, read back with the same truncation), one thread moves one
+// 8-byte group of four ids, so a warp reads 256 B of table rows and writes 512 B / 1 KB of output
+// fully coalesced.
+#include "mot_common.cuh"
+
+namespace mot {
+
+template <int TTB, typename OutT>
+__global__ void __launch_bounds__(256) ttb_expand_kernel(const int32_t* __restrict__ tok, long long n, const void* __restrict__ ttb,
+                                                        int V, int bpt, OutT* __restrict__ out) {
+  const long long total = n * bpt;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (TTB == MOT_TTB_I16 && (bpt & 3) == 0) {
+    // four ids per thread: one 8-byte table load, one 16/32-byte store
+    const long long groups = total >> 2;
+    const int gpt = bpt >> 2;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+      const long long t = g / gpt;
+      const int k = (int)(g - t * gpt);
+      const int tv = min(max(__ldg(tok + t), 0), V - 1);
+      const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const short*>(ttb) + (size_t)tv * bpt) + k);
+      const OutT a = (OutT)(short)(r.x & 0xffffu), b = (OutT)(short)(r.x >> 16), c = (OutT)(short)(r.y & 0xffffu),
+                 d = (OutT)(short)(r.y >> 16);
+      OutT* o = out + (g << 2);
+      o[0] = a; o[1] = b; o[2] = c; o[3] = d;
+    }
+    return;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long t = i / bpt;
+    const int k = (int)(i - t * bpt);
+    const int tv = min(max(__ldg(tok + t), 0), V - 1);
+    const size_t e = (size_t)tv * bpt + k;
+    long long id;
+    if (TTB == MOT_TTB_I16) id = __ldg(reinterpret_cast<const short*>(ttb) + e);
+    else if (TTB == MOT_TTB_F32) id = (long long)__ldg(reinterpret_cast<const float*>(ttb) + e);  // trunc, like .to(int64)
+    else id = (long long)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ttb)[e]);
+    out[i] = (OutT)id;
+  }
+}
+
+template <int TTB>
+static int launch_expand(const int32_t* tok, long long n, const void* ttb, int V, int bpt, void* out, int out_i64,
+                         cudaStream_t s) {
+  int sms = 0, optin = 0;
+  if (int rc = device_props(&sms, &optin)) return rc;
+  const long long total = n * bpt;
+  long long blocks = (total / 4 + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  if (blocks < 1) blocks = 1;
+  if (out_i64) ttb_expand_kernel<TTB, long long><<<(unsigned)blocks, 256, 0, s>>>(tok, n, ttb, V, bpt, reinterpret_cast<long long*>(out));
+  else ttb_expand_kernel<TTB, int><<<(unsigned)blocks, 256, 0, s>>>(tok, n, ttb, V, bpt, reinterpret_cast<int*>(out));
+  count_launch();
+  return check_launch();
+}
+
+}  // namespace mot
+
+extern "C" int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
+                              int32_t ttb_dtype, void* out, int32_t out_i64, void* stream) {
+  if (n < 0 || tok_vocab <= 0 || bpt <= 0) return MOT_ERR_BAD_ARG;
+  if (n == 0) return MOT_OK;
+  if (!tok || !ttb || !out) return MOT_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(ttb) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return MOT_ERR_MISALIGNED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (ttb_dtype) {
+    case MOT_TTB_I16: return mot::launch_expand<MOT_TTB_I16>(tok, n, ttb, tok_vocab, bpt, out, out_i64, s);
+    case MOT_TTB_F32: return mot::launch_expand<MOT_TTB_F32>(tok, n, ttb, tok_vocab, bpt, out, out_i64, s);
+    case MOT_TTB_BF16: return mot::launch_expand<MOT_TTB_BF16>(tok, n, ttb, tok_vocab, bpt, out, out_i64, s);
+  }
+  return MOT_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,213 @@
+"""Functional API over libmot_b200.so: ttb expansion and the fused byte-mix
+embedding with autograd.  Tensors must live on a CUDA (B200) device; CPU tensors
+raise -- there is no fallback path."""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+FP32_EPS = float(torch.finfo(torch.float32).eps)  # F.rms_norm's default eps (train_gpt.py:172-173)
+
+_COMBINE = {"add": L.ADD, "concat": L.CONCAT, "tok_only": L.TOK_ONLY, "bytes_only": L.BYTES_ONLY, "mean": L.MEAN}
+_DTYPE = {torch.bfloat16: L.BF16, torch.float32: L.F32}
+_TTB_DTYPE = {torch.int16: L.TTB_I16, torch.float32: L.TTB_F32, torch.bfloat16: L.TTB_BF16}
+
+
+@dataclasses.dataclass(frozen=True)
+class MixSpec:
+    """Which member of the mixin catalogue the fused kernel computes."""
+    combine: str = "add"          # add | concat | tok_only | bytes_only | mean
+    tok_norm: bool = False        # rms_norm(E_tok[tok])            runs/7:317
+    byte_norm: bool = False       # rms_norm(E_byte[id]) per byte   runs/7:318
+    out_norm: bool = True         # rms_norm(mixed row)             runs/71:230
+    bytes_first: bool = False     # concat order [bytes | tok]      mathblations/model.py:267
+    slot_major: bool = False      # byte ids are [bpt, T]           runs/71:479
+    ttb_scramble: bool = False    # ids from ttb with the `.view(bpt,-1)` index map
+    eps: float = FP32_EPS
+
+
+def _require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mot_b200: tensors must be on a CUDA device (no CPU fallback)")
+        if dev is not None and t.device != dev:
+            raise RuntimeError("mot_b200: tensors are on different devices")
+        dev = t.device
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """tokens_to_bytes (spt/data_creation.py:61-67): [B,T] -> [B, T*bpt], [T] -> [1, T*bpt].
+
+    `ttb` is the [V, bpt] table: int16 (native) or the reference's float containers (fp32
+    nn.Embedding weight, or the bf16-cast weight of the runs with its id-rounding quirk)."""
+    dev = _require_cuda(tokens, ttb)
+    if ttb.dtype not in _TTB_DTYPE or ttb.dim() != 2:
+        raise NotImplementedError(f"mot_b200.ttb_expand: ttb must be a 2-D int16/float32/bfloat16 table, got {ttb.dtype}")
+    if out_dtype not in (torch.int64, torch.int32):
+        raise NotImplementedError("mot_b200.ttb_expand: out_dtype must be int64 or int32")
+    tok = tokens.to(torch.int32).contiguous()
+    ttb = ttb.contiguous()
+    V, bpt = ttb.shape
+    n = tok.numel()
+    out = torch.empty((n, bpt), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_ttb_expand(_ptr(tok), n, _ptr(ttb), V, bpt, _TTB_DTYPE[ttb.dtype], _ptr(out),
+                                    1 if out_dtype == torch.int64 else 0, _stream(dev))
+    L.check(rc, "mot_ttb_expand")
+    if tokens.dim() == 2:
+        return out.view(tokens.shape[0], -1)
+    return out.view(1, -1)
+
+
+def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Optional[torch.Tensor],
+              ttb: Optional[torch.Tensor], has_lam: bool, seq_len: int = 0) -> L.MotDesc:
+    ref = E_tok if E_tok is not None else E_byte
+    if ref.dtype not in _DTYPE:
+        raise NotImplementedError(f"mot_b200: embedding dtype {ref.dtype} is not supported (bf16 / fp32 only)")
+    if spec.combine not in _COMBINE:
+        raise NotImplementedError(f"mot_b200: unknown combine mode {spec.combine!r}")
+    has_tok, has_bytes = spec.combine != "bytes_only", spec.combine != "tok_only"
+    Dt = E_tok.shape[1] if has_tok else 0
+    bd = E_byte.shape[1] if has_bytes else 0
+    if spec.combine in ("add", "tok_only", "mean"):
+        Do = Dt
+    elif spec.combine == "concat":
+        Do = Dt + bpt * bd
+    else:
+        Do = bpt * bd
+    flags = 0
+    flags |= L.F_TOK_NORM if spec.tok_norm else 0
+    flags |= L.F_BYTE_NORM if spec.byte_norm else 0
+    flags |= L.F_OUT_NORM if spec.out_norm else 0
+    flags |= L.F_BYTES_FIRST if spec.bytes_first else 0
+    flags |= L.F_HAS_LAMBDAS if has_lam else 0
+    ttb_dtype = 0
+    if has_bytes:
+        if ids is None:
+            if ttb is None:
+                raise RuntimeError("mot_b200: need byte ids or a ttb table")
+            flags |= L.F_IDS_FROM_TTB
+            flags |= L.F_TTB_SCRAMBLE if spec.ttb_scramble else 0
+            ttb_dtype = _TTB_DTYPE[ttb.dtype]
+        else:
+            flags |= L.F_SLOT_MAJOR if spec.slot_major else 0
+            flags |= L.F_IDS_I64 if ids.dtype == torch.int64 else 0
+    return L.MotDesc(L.ABI_VERSION, _DTYPE[ref.dtype], n_tokens, seq_len,
+                     E_tok.shape[0] if has_tok else 0, E_byte.shape[0] if has_bytes else 0, bpt if has_bytes else 0,
+                     Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps)
+
+
+def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out) -> None:
+    """mot_embed_fwd on caller-allocated tensors (no allocation, no sync; CUDA-graph capturable)."""
+    dev = out.device
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_embed_fwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                   _ptr(out), _stream(dev))
+    L.check(rc, "mot_embed_fwd")
+
+
+def embed_workspace_bytes(desc: L.MotDesc) -> int:
+    return int(L.lib().mot_embed_workspace_bytes(desc))
+
+
+def embed_plan(desc: L.MotDesc, tok, ws) -> None:
+    dev = ws.device
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_embed_plan(desc, _ptr(tok), _ptr(ws), ws.numel(), _stream(dev))
+    L.check(rc, "mot_embed_plan")
+
+
+def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
+                       plan_ready: bool = False) -> None:
+    """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten."""
+    dev = grad_out.device
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                   _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
+                                   1 if plan_ready else 0, _stream(dev))
+    L.check(rc, "mot_embed_bwd")
+
+
+class _MotEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: MixSpec, bpt: int, seq_len: int, tokens, byte_ids, ttb, E_tok, E_byte, lam):
+        dev = _require_cuda(tokens, byte_ids, ttb, E_tok, E_byte, lam)
+        tok = None
+        if tokens is not None:
+            tok = tokens.reshape(-1)
+            tok = tok if tok.dtype == torch.int32 else tok.to(torch.int32)
+            tok = tok.contiguous()
+        ids = None
+        if byte_ids is not None:
+            if byte_ids.dtype not in (torch.int32, torch.int64):
+                raise NotImplementedError("mot_b200: byte ids must be int32 or int64")
+            ids = byte_ids.contiguous()
+        n = tok.numel() if tok is not None else ids.numel() // bpt
+        if ids is not None and ids.numel() != n * bpt:
+            raise RuntimeError(f"mot_b200: byte ids have {ids.numel()} entries, expected {n}*{bpt}")
+        E_tok_c = E_tok.contiguous() if E_tok is not None else None
+        E_byte_c = E_byte.contiguous() if E_byte is not None else None
+        if E_tok_c is not None and E_byte_c is not None and E_tok_c.dtype != E_byte_c.dtype:
+            raise NotImplementedError("mot_b200: token and byte tables must share one dtype")
+        lam_c = lam.detach().to(torch.float32).contiguous() if lam is not None else None
+        desc = make_desc(spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=ttb, has_lam=lam is not None, seq_len=seq_len)
+        ref = E_tok_c if E_tok_c is not None else E_byte_c
+        out = torch.empty((n, desc.out_dim), dtype=ref.dtype, device=dev)
+        embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out)
+        ctx.desc, ctx.dev = desc, dev
+        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)])
+        ctx.present = [t is not None for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)]
+        ctx.lam_dtype = lam.dtype if lam is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = [t if ok else None for t, ok in zip(ctx.saved_tensors, ctx.present)]
+        tok, ids, ttb, E_tok, E_byte, lam = saved
+        desc, dev = ctx.desc, ctx.dev
+        g = grad_out.contiguous()
+        if g.dtype != (E_tok if E_tok is not None else E_byte).dtype:
+            g = g.to((E_tok if E_tok is not None else E_byte).dtype)
+        gE_tok = torch.empty_like(E_tok) if E_tok is not None else None
+        gE_byte = torch.empty_like(E_byte) if E_byte is not None else None
+        g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
+        ws = torch.empty(embed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
+        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws)
+        if g_lam is not None:
+            g_lam = g_lam.to(ctx.lam_dtype)
+        return None, None, None, None, None, None, gE_tok, gE_byte, g_lam
+
+
+def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], E_tok: Optional[torch.Tensor],
+              E_byte: Optional[torch.Tensor], spec: MixSpec, *, bpt: int = 16, lam: Optional[torch.Tensor] = None,
+              ttb: Optional[torch.Tensor] = None, seq_len: int = 0) -> torch.Tensor:
+    """Fused gather + pool + combine + norm.  Returns [n_tokens, out_dim] in the table dtype.
+
+    tokens   int32/int64 [..] (flattened); byte_ids int32/int64 with n_tokens*bpt entries, token-major
+    ([.., T*bpt]) or slot-major ([bpt, T], spec.slot_major); byte_ids=None derives the ids from `ttb`
+    inside the kernel.  lam = float tensor [2] = (lam_tok, lam_byte) or None."""
+    return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam)
+
+
+def launch_count() -> int:
+    return int(L.lib().mot_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.lib().mot_launch_count_reset()
