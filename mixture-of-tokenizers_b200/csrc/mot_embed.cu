@@ -11,70 +11,72 @@ __global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, i
     atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
 }
 
-// single CTA, 1024 threads: four exclusive scans over the vocabulary in one pass
+// Four exclusive scans over the vocabulary (segment offsets, work-item offsets, hot-row offsets, partial-slot
+// offsets).  One CTA per 1024-entry tile: each CTA first sums every entry in front of its tile (coalesced,
+// <= 49 independent loads per thread, all L2 hits), then scans its own tile with warp shuffles.
+__device__ __forceinline__ int4 plan_quad(int c, int L) {
+  const int nch = (c + L - 1) / L;
+  return make_int4(c, nch, nch > 1 ? 1 : 0, nch > 1 ? nch : 0);
+}
+__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ int4 shfl_up4(int4 v, int o) {
+  return make_int4(__shfl_up_sync(0xffffffffu, v.x, o), __shfl_up_sync(0xffffffffu, v.y, o),
+                   __shfl_up_sync(0xffffffffu, v.z, o), __shfl_up_sync(0xffffffffu, v.w, o));
+}
+__device__ __forceinline__ int4 shfl_xor4(int4 v, int o) {
+  return make_int4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
+                   __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
+}
+
 __global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
   __shared__ int4 wsum[32];
-  __shared__ int4 carry_s;
+  __shared__ int4 wcarry[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (p.V + 1023) / 1024;
-  const int v0 = tid * per, v1 = min(v0 + per, p.V);
-  int4 loc = make_int4(0, 0, 0, 0);
-  for (int v = v0; v < v1; ++v) {
-    const int c = p.cnt[v];
-    const int nch = (c + p.L - 1) / p.L;
-    loc.x += c;
-    loc.y += nch;
-    loc.z += (nch > 1);
-    loc.w += (nch > 1) ? nch : 0;
-  }
-  int4 inc = loc;  // inclusive scan over lanes
+  const int base = blockIdx.x * 1024;
+  // (1) carry-in: sum of everything in front of this tile
+  int4 carry = make_int4(0, 0, 0, 0);
+  for (int v = tid; v < base; v += 1024) carry = add4(carry, plan_quad(p.cnt[v], p.L));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) carry = add4(carry, shfl_xor4(carry, o));
+  if (lane == 0) wcarry[warp] = carry;
+  // (2) inclusive scan of the tile
+  const int v = base + tid;
+  const int4 mine = v < p.V ? plan_quad(p.cnt[v], p.L) : make_int4(0, 0, 0, 0);
+  int4 inc = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int4 t;
-    t.x = __shfl_up_sync(0xffffffffu, inc.x, o);
-    t.y = __shfl_up_sync(0xffffffffu, inc.y, o);
-    t.z = __shfl_up_sync(0xffffffffu, inc.z, o);
-    t.w = __shfl_up_sync(0xffffffffu, inc.w, o);
-    if (lane >= o) { inc.x += t.x; inc.y += t.y; inc.z += t.z; inc.w += t.w; }
+    const int4 t = shfl_up4(inc, o);
+    if (lane >= o) inc = add4(inc, t);
   }
   if (lane == 31) wsum[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int4 w = wsum[lane];
+    int4 c = wcarry[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = add4(c, shfl_xor4(c, o));  // total carry, all lanes
+    const int4 w = wsum[lane];
     int4 wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int4 t;
-      t.x = __shfl_up_sync(0xffffffffu, wi.x, o);
-      t.y = __shfl_up_sync(0xffffffffu, wi.y, o);
-      t.z = __shfl_up_sync(0xffffffffu, wi.z, o);
-      t.w = __shfl_up_sync(0xffffffffu, wi.w, o);
-      if (lane >= o) { wi.x += t.x; wi.y += t.y; wi.z += t.z; wi.w += t.w; }
+      const int4 t = shfl_up4(wi, o);
+      if (lane >= o) wi = add4(wi, t);
     }
-    wsum[lane] = make_int4(wi.x - w.x, wi.y - w.y, wi.z - w.z, wi.w - w.w);  // exclusive warp offsets
-    if (lane == 31) carry_s = wi;                                            // totals
+    wsum[lane] = make_int4(c.x + wi.x - w.x, c.y + wi.y - w.y, c.z + wi.z - w.z, c.w + wi.w - w.w);  // exclusive, incl. carry
   }
   __syncthreads();
   const int4 wo = wsum[warp];
-  int4 run = make_int4(wo.x + inc.x - loc.x, wo.y + inc.y - loc.y, wo.z + inc.z - loc.z, wo.w + inc.w - loc.w);
-  for (int v = v0; v < v1; ++v) {
-    const int c = p.cnt[v];
-    const int nch = (c + p.L - 1) / p.L;
-    p.off[v] = run.x;
-    p.item_off[v] = run.y;
-    p.hot_off[v] = run.z;
-    p.pslot_off[v] = run.w;
-    run.x += c;
-    run.y += nch;
-    run.z += (nch > 1);
-    run.w += (nch > 1) ? nch : 0;
+  const int4 ex = make_int4(wo.x + inc.x - mine.x, wo.y + inc.y - mine.y, wo.z + inc.z - mine.z, wo.w + inc.w - mine.w);
+  if (v < p.V) {
+    p.off[v] = ex.x;
+    p.item_off[v] = ex.y;
+    p.hot_off[v] = ex.z;
+    p.pslot_off[v] = ex.w;
   }
-  if (tid == 0) {
-    const int4 tot = carry_s;
-    p.off[p.V] = tot.x;
-    p.item_off[p.V] = tot.y;
-    p.hot_off[p.V] = tot.z;
-    p.pslot_off[p.V] = tot.w;
+  if (v == p.V - 1) {  // totals
+    p.off[p.V] = ex.x + mine.x;
+    p.item_off[p.V] = ex.y + mine.y;
+    p.hot_off[p.V] = ex.z + mine.z;
+    p.pslot_off[p.V] = ex.w + mine.w;
   }
 }
 
@@ -216,7 +218,7 @@ static int run_plan(const EmbedParams& p, cudaStream_t s) {
   long long hb = (p.N + 255) / 256;
   if (hb > 2048) hb = 2048;
   plan_hist_kernel<<<(unsigned)hb, 256, 0, s>>>(p.tok, p.N, p.V, p.cnt);
-  plan_scan_kernel<<<1, 1024, 0, s>>>(p);
+  plan_scan_kernel<<<(unsigned)((p.V + 1023) / 1024), 1024, 0, s>>>(p);
   const long long m = p.N > p.V ? p.N : p.V;
   plan_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(p);
   count_launch(3);
@@ -237,6 +239,7 @@ extern "C" size_t mot_embed_workspace_bytes(const MotDesc* d) {
 extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream) {
   if (int rc = validate(d)) return rc;
+  if (d->n_tokens == 0) return MOT_OK;  // empty batch: nothing to write (empty tensors have null pointers)
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
   if (!out || (has_tok && (!tok || !E_tok)) || (has_bytes && !E_byte)) return MOT_ERR_BAD_ARG;
   if (has_bytes) {
@@ -245,7 +248,6 @@ extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* b
   }
   if ((d->flags & MOT_F_HAS_LAMBDAS) && !lam) return MOT_ERR_BAD_ARG;
   if (!aligned16(out) || !aligned16(E_tok) || !aligned16(E_byte)) return MOT_ERR_MISALIGNED;
-  if (d->n_tokens == 0) return MOT_OK;
   EmbedParams p;
   fill_params(d, p);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam; p.out = out;
@@ -276,9 +278,20 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
                              int32_t plan_ready, void* stream) {
   if (int rc = validate(d)) return rc;
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
+  if (has_tok && !gE_tok) return MOT_ERR_BAD_ARG;
+  if (has_bytes && !gE_byte) return MOT_ERR_BAD_ARG;
+  if (!aligned16(gE_tok) || !aligned16(gE_byte)) return MOT_ERR_MISALIGNED;
+  if (d->n_tokens == 0) {  // nothing gathered: dense zero grads
+    cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
+    const size_t esz0 = d->dtype == MOT_BF16 ? 2 : 4;
+    if (has_tok && cudaMemsetAsync(gE_tok, 0, (size_t)d->tok_vocab * d->tok_dim * esz0, s0) != cudaSuccess) return check_launch();
+    if (has_bytes && cudaMemsetAsync(gE_byte, 0, (size_t)d->byte_vocab * d->byte_dim * esz0, s0) != cudaSuccess) return check_launch();
+    if (g_lam && cudaMemsetAsync(g_lam, 0, 8, s0) != cudaSuccess) return check_launch();
+    return MOT_OK;
+  }
   if (!grad_out || !workspace) return MOT_ERR_BAD_ARG;
-  if (has_tok && (!tok || !E_tok || !gE_tok)) return MOT_ERR_BAD_ARG;
-  if (has_bytes && (!E_byte || !gE_byte)) return MOT_ERR_BAD_ARG;
+  if (has_tok && (!tok || !E_tok)) return MOT_ERR_BAD_ARG;
+  if (has_bytes && !E_byte) return MOT_ERR_BAD_ARG;
   if (has_bytes) {
     if (d->flags & MOT_F_IDS_FROM_TTB) { if (!ttb || !tok) return MOT_ERR_BAD_ARG; }
     else if (!byte_ids) return MOT_ERR_BAD_ARG;
@@ -296,12 +309,6 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
   p.gout = grad_out; p.gE_tok = gE_tok; p.gE_byte = gE_byte; p.g_lam = g_lam;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
-  if (d->n_tokens == 0) {  // nothing gathered: dense zero grads
-    if (has_tok && cudaMemsetAsync(gE_tok, 0, (size_t)d->tok_vocab * d->tok_dim * esz, s) != cudaSuccess) return check_launch();
-    if (has_bytes && cudaMemsetAsync(gE_byte, 0, (size_t)d->byte_vocab * d->byte_dim * esz, s) != cudaSuccess) return check_launch();
-    if (g_lam && cudaMemsetAsync(g_lam, 0, 8, s) != cudaSuccess) return check_launch();
-    return MOT_OK;
-  }
   if (!plan_ready) {
     if (cudaMemsetAsync(workspace, 0, w.off, s) != cudaSuccess) return check_launch();
     if (int rc = run_plan(p, s)) return rc;

@@ -15,6 +15,7 @@
 // 512 B (bf16) segment per `it`.  The byte table lives in shared memory (staged once per CTA with a
 // bulk async copy), so the only HBM streams are token rows, grad rows, output rows and the dense grad.
 #pragma once
+#include <cstdlib>
 #include "mot_common.cuh"
 
 namespace mot {
@@ -51,6 +52,8 @@ struct EmbedParams {
   int V, Vb, bpt, Dt, bd, Do, combine, flags, ttb_dtype;
   int n_chunks;  // Do / 8
   int L;         // occurrences per work item
+  int acc_stride;  // floats per row of the shared-memory accumulators (bd + 2: spreads rows over banks)
+  int tab_smem;  // 1: byte table staged in shared memory; 0: too large, rows read through L1/L2
   float eps;
 };
 
@@ -129,22 +132,29 @@ __device__ __forceinline__ int fetch_id(const EmbedParams& p, long long pos, int
 // Stage E_byte into shared memory with one bulk async copy per 32 KB and compute the per-row
 // rms scale (byte_norm).  rs[r] = rsqrt(mean(row^2) + eps) or 1.
 template <typename T>
+__device__ __forceinline__ typename Vec8<T>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
+  return p.tab_smem ? Vec8<T>::lds_raw(tab + off) : Vec8<T>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
+}
+
+template <typename T>
 __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar) {
-  const uint32_t bytes = (uint32_t)p.Vb * p.bd * sizeof(T);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, bytes);
-    for (uint32_t done = 0; done < bytes;) {
-      const uint32_t n = min(bytes - done, 32768u);
-      bulk_g2s(reinterpret_cast<char*>(tab) + done, reinterpret_cast<const char*>(p.E_byte) + done, n, bar);
-      done += n;
+  if (p.tab_smem) {
+    const uint32_t bytes = (uint32_t)p.Vb * p.bd * sizeof(T);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      for (uint32_t done = 0; done < bytes;) {
+        const uint32_t n = min(bytes - done, 32768u);
+        bulk_g2s(reinterpret_cast<char*>(tab) + done, reinterpret_cast<const char*>(p.E_byte) + done, n, bar);
+        done += n;
+      }
+    }
+    mbar_wait(bar, 0);
   }
-  mbar_wait(bar, 0);
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = lane_id();
   const bool bn = (p.flags & MOT_F_BYTE_NORM) != 0;
   for (int r = warp; r < p.Vb; r += nw) {
@@ -152,7 +162,7 @@ __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64
     if (bn) {
       for (int c = lane; c < p.bd / kChunk; c += 32) {
         float v[8];
-        Vec8<T>::unpack(Vec8<T>::lds_raw(tab + (size_t)r * p.bd + c * kChunk), v);
+        Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)r * p.bd + c * kChunk), v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
       }
@@ -161,6 +171,34 @@ __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64
     if (lane == 0) rs[r] = bn ? rsqrtf(ss / (float)p.bd + p.eps) : 1.f;
   }
   __syncthreads();
+}
+
+// acc[0..8) += v[0..8).  Shared memory has no native fp32 atomic add (atomicAdd lowers to one
+// load + CAS spin loop PER element, 24 serial round trips per occurrence); here the four 64-bit words
+// are read once, the four CAS are issued back to back and only the losers retry.
+__device__ __forceinline__ void smem_add8(float* a, const float (&v)[8]) {
+  unsigned long long* a2 = reinterpret_cast<unsigned long long*>(a);
+  unsigned long long old[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) old[q] = *reinterpret_cast<volatile unsigned long long*>(a2 + q);
+  unsigned pending = 0xFu;
+  while (pending) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pending & (1u << q)) {
+        const float lo = __uint_as_float((unsigned)old[q]) + v[2 * q];
+        const float hi = __uint_as_float((unsigned)(old[q] >> 32)) + v[2 * q + 1];
+        const unsigned long long nw = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+        const unsigned long long prev = atomicCAS(a2 + q, old[q], nw);
+        if (prev == old[q]) pending &= ~(1u << q);
+        else old[q] = prev;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
+  atomicAdd(reinterpret_cast<float4*>(a), make_float4(v[0], v[1], v[2], v[3]));      // RED.E.ADD.F32x4
+  atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -178,8 +216,8 @@ template <typename T, int CPL>
 __global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
-  T* tab = reinterpret_cast<T*>(smem_raw);
-  float* rs = reinterpret_cast<float*>(smem_raw + align_up((size_t)p.Vb * p.bd * sizeof(T), 128));
+  float* rs = reinterpret_cast<float*>(smem_raw);
+  T* tab = reinterpret_cast<T*>(smem_raw + align_up((size_t)p.Vb * sizeof(float), 128));
   const bool has_tok = p.combine != MOT_BYTES_ONLY;
   const bool has_bytes = p.combine != MOT_TOK_ONLY;
   if (has_bytes) stage_byte_table<T>(p, tab, rs, &bar);
@@ -245,7 +283,7 @@ __global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams 
             const int id = __shfl_sync(0xffffffffu, ld.idreg, k);
             if (cm[it].slot == -2) {
               float b[8];
-              Vec8<T>::unpack(Vec8<T>::lds_raw(tab + (size_t)id * p.bd + cm[it].boff), b);
+              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               const float bs = lam_b * rs[id];
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
@@ -255,7 +293,7 @@ __global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams 
           const int id = __shfl_sync(0xffffffffu, ld.idreg, cm[it].slot & 31);
           if (cm[it].slot >= 0) {
             float b[8];
-            Vec8<T>::unpack(Vec8<T>::lds_raw(tab + (size_t)id * p.bd + cm[it].boff), b);
+            Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
             const float bs = lam_b * rs[id];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
@@ -334,19 +372,21 @@ template <typename T, int CPL, bool SMEM_ACC>
 __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
-  const size_t tab_bytes = align_up((size_t)p.Vb * p.bd * sizeof(T), 128);
-  T* tab = reinterpret_cast<T*>(smem_raw);
-  float* rs = reinterpret_cast<float*>(smem_raw + tab_bytes);
-  float* acc = reinterpret_cast<float*>(smem_raw + tab_bytes + align_up((size_t)p.Vb * sizeof(float), 128));
+  const size_t rs_bytes = align_up((size_t)p.Vb * sizeof(float), 128);
+  const size_t tab_bytes = p.tab_smem ? align_up((size_t)p.Vb * p.bd * sizeof(T), 128) : 0;
+  float* rs = reinterpret_cast<float*>(smem_raw);
+  T* tab = reinterpret_cast<T*>(smem_raw + rs_bytes);
+  float* acc = reinterpret_cast<float*>(smem_raw + rs_bytes + tab_bytes);
   const bool has_tok = p.combine != MOT_BYTES_ONLY;
   const bool has_bytes = p.combine != MOT_TOK_ONLY;
-  const int nacc = p.Vb * p.bd;
+  const int nacc = p.Vb * p.acc_stride;
   if (has_bytes) {
     if (SMEM_ACC)
       for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0.f;
     stage_byte_table<T>(p, tab, rs, &bar);  // ends with __syncthreads()
   }
   float* accp = SMEM_ACC ? acc : p.byte_acc;
+  const int astride = SMEM_ACC ? p.acc_stride : p.bd;
 
   const int lane = lane_id();
   const int nw = blockDim.x >> 5;
@@ -402,7 +442,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
           const int id = __shfl_sync(0xffffffffu, idreg, k);
           if (cm[it].slot == -2) {
             float b[8];
-            Vec8<T>::unpack(Vec8<T>::lds_raw(tab + (size_t)id * p.bd + cm[it].boff), b);
+            Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
             const float r = rs[id];
 #pragma unroll
             for (int e = 0; e < 8; ++e) bhat[e] += r * b[e];
@@ -412,7 +452,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         const int id = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
         if (cm[it].slot >= 0) {
           float b[8];
-          Vec8<T>::unpack(Vec8<T>::lds_raw(tab + (size_t)id * p.bd + cm[it].boff), b);
+          Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
           const float r = rs[id];
 #pragma unroll
           for (int e = 0; e < 8; ++e) bhat[e] = r * b[e];
@@ -467,21 +507,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
           for (int e = 0; e < 8; ++e) dlam_b += inv_pool * dz[e] * bhat[e];
         }
+        float bv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bv[e] = lam_b_eff * dz[e];
         if (p.combine == MOT_MEAN) {
           for (int k = 0; k < p.bpt; ++k) {
             const int id = __shfl_sync(0xffffffffu, o.idreg, k);
             if (cm[it].slot == -2) {
-              float* a = accp + (size_t)id * p.bd + cm[it].boff;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) atomicAdd(a + e, lam_b_eff * dz[e]);
+              float* a = accp + (size_t)id * astride + cm[it].boff;
+              if (SMEM_ACC) smem_add8(a, bv); else gmem_add8(a, bv);
             }
           }
         } else {
           const int id = __shfl_sync(0xffffffffu, o.idreg, cm[it].slot & 31);
           if (cm[it].slot >= 0) {
-            float* a = accp + (size_t)id * p.bd + cm[it].boff;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(a + e, lam_b_eff * dz[e]);
+            float* a = accp + (size_t)id * astride + cm[it].boff;
+            if (SMEM_ACC) smem_add8(a, bv); else gmem_add8(a, bv);
           }
         }
       }
@@ -585,10 +626,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   // ---- CTA epilogue: flush the byte accumulators and the lambda partials ----
   if (has_bytes && SMEM_ACC) {
     __syncthreads();
-    for (int i = threadIdx.x * 4; i < nacc; i += blockDim.x * 4) {
-      const float4 a = *reinterpret_cast<const float4*>(acc + i);
-      if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)
-        atomicAdd(reinterpret_cast<float4*>(p.byte_acc + i), a);
+    const int c4 = p.bd / 4;  // float4 groups per row (bd is a multiple of 8)
+    for (int i = threadIdx.x; i < p.Vb * c4; i += blockDim.x) {
+      const int r = i / c4, c = (i - r * c4) * 4;
+      const float2 lo = *reinterpret_cast<const float2*>(acc + (size_t)r * p.acc_stride + c);
+      const float2 hi = *reinterpret_cast<const float2*>(acc + (size_t)r * p.acc_stride + c + 2);
+      if (lo.x != 0.f || lo.y != 0.f || hi.x != 0.f || hi.y != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(p.byte_acc + (size_t)r * p.bd + c), make_float4(lo.x, lo.y, hi.x, hi.y));
     }
   }
   if (has_lam) {
@@ -699,23 +743,26 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
 }
 
 
-inline size_t fwd_smem_bytes(const EmbedParams& p, size_t esz) {
+inline size_t smem_bytes(const EmbedParams& p, size_t esz, bool tab, bool acc) {
   if (p.combine == MOT_TOK_ONLY) return 0;
-  return align_up((size_t)p.Vb * p.bd * esz, 128) + align_up((size_t)p.Vb * 4, 128);
-}
-inline size_t bwd_smem_bytes(const EmbedParams& p, size_t esz, bool smem_acc) {
-  if (p.combine == MOT_TOK_ONLY) return 0;
-  return fwd_smem_bytes(p, esz) + (smem_acc ? align_up((size_t)p.Vb * p.bd * 4, 128) : 0);
+  return align_up((size_t)p.Vb * 4, 128) + (tab ? align_up((size_t)p.Vb * p.bd * esz, 128) : 0) +
+         (acc ? align_up((size_t)p.Vb * (p.bd + 2) * 4, 128) : 0);
 }
 
 template <typename T, int CPL>
-static int launch_fwd(const EmbedParams& p, cudaStream_t s) {
+static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
-  const size_t smem = fwd_smem_bytes(p, sizeof(T));
-  if (smem > (size_t)optin) return MOT_ERR_UNSUPPORTED;
+  EmbedParams p = p_in;
+  p.tab_smem = 1;
+  size_t smem = smem_bytes(p, sizeof(T), true, false);
+  if (smem + 1024 > (size_t)optin) {  // table larger than one SM's shared memory: gather rows through L1/L2
+    p.tab_smem = 0;
+    smem = smem_bytes(p, sizeof(T), false, false);
+  }
   auto kern = mot_fwd_kernel<T, CPL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFwdThreads, smem);
   if (occ < 1) occ = 1;
@@ -733,15 +780,25 @@ static int launch_fwd(const EmbedParams& p, cudaStream_t s) {
 
 
 template <typename T, int CPL>
-static int launch_bwd(const EmbedParams& p, cudaStream_t s) {
+static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
+  EmbedParams p = p_in;
+  // preference: table + fp32 accumulators in shared memory; else accumulators in the L2-resident
+  // scratch (fp32 atomics); else the table through L1/L2 as well
   bool smem_acc = true;
-  size_t smem = bwd_smem_bytes(p, sizeof(T), true);
-  if (smem + 1024 > (size_t)optin) {
-    smem_acc = false;  // accumulators too large for one SM: fp32 atomics straight to the L2-resident scratch
-    smem = bwd_smem_bytes(p, sizeof(T), false);
-    if (smem + 1024 > (size_t)optin) return MOT_ERR_UNSUPPORTED;
+  p.tab_smem = 1;
+  p.acc_stride = p.bd + 2;
+  static const char* acc_env = getenv("MOT_BWD_ACC");  // debug knob: "global" forces the L2-atomics path
+  const bool force_global = acc_env && acc_env[0] == 'g';
+  size_t smem = smem_bytes(p, sizeof(T), true, true);
+  if (force_global || smem + 1024 > (size_t)optin) {
+    smem_acc = false;
+    smem = smem_bytes(p, sizeof(T), true, false);
+    if (smem + 1024 > (size_t)optin) {
+      p.tab_smem = 0;
+      smem = smem_bytes(p, sizeof(T), false, false);
+    }
   }
   auto kern = smem_acc ? mot_bwd_kernel<T, CPL, true> : mot_bwd_kernel<T, CPL, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
