@@ -11,96 +11,59 @@ __global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, i
     atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
 }
 
-// Four exclusive scans over the vocabulary (segment offsets, work-item offsets, hot-row offsets, partial-slot
-// offsets).  One CTA per 1024-entry tile: each CTA first sums every entry in front of its tile (coalesced,
-// <= 49 independent loads per thread, all L2 hits), then scans its own tile with warp shuffles.
-__device__ __forceinline__ int4 plan_quad(int c, int L) {
-  const int nch = (c + L - 1) / L;
-  return make_int4(c, nch, nch > 1 ? 1 : 0, nch > 1 ? nch : 0);
-}
-__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ int4 shfl_up4(int4 v, int o) {
-  return make_int4(__shfl_up_sync(0xffffffffu, v.x, o), __shfl_up_sync(0xffffffffu, v.y, o),
-                   __shfl_up_sync(0xffffffffu, v.z, o), __shfl_up_sync(0xffffffffu, v.w, o));
-}
-__device__ __forceinline__ int4 shfl_xor4(int4 v, int o) {
-  return make_int4(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o),
-                   __shfl_xor_sync(0xffffffffu, v.z, o), __shfl_xor_sync(0xffffffffu, v.w, o));
-}
-
+// Exclusive scan of the histogram -> segment offsets.  One CTA per 1024-entry tile: each CTA first sums every
+// entry in front of its tile (coalesced, <= 49 independent loads per thread, all L2 hits), then scans its own
+// tile with warp shuffles.
 __global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
-  __shared__ int4 wsum[32];
-  __shared__ int4 wcarry[32];
+  __shared__ int wsum[32];
+  __shared__ int wcarry[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int base = blockIdx.x * 1024;
-  // (1) carry-in: sum of everything in front of this tile
-  int4 carry = make_int4(0, 0, 0, 0);
-  for (int v = tid; v < base; v += 1024) carry = add4(carry, plan_quad(p.cnt[v], p.L));
+  int carry = 0;
+  for (int v = tid; v < base; v += 1024) carry += p.cnt[v];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) carry = add4(carry, shfl_xor4(carry, o));
+  for (int o = 16; o > 0; o >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, o);
   if (lane == 0) wcarry[warp] = carry;
-  // (2) inclusive scan of the tile
   const int v = base + tid;
-  const int4 mine = v < p.V ? plan_quad(p.cnt[v], p.L) : make_int4(0, 0, 0, 0);
-  int4 inc = mine;
+  const int mine = v < p.V ? p.cnt[v] : 0;
+  int inc = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int4 t = shfl_up4(inc, o);
-    if (lane >= o) inc = add4(inc, t);
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
   if (lane == 31) wsum[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int4 c = wcarry[lane];
+    int c = wcarry[lane];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c = add4(c, shfl_xor4(c, o));  // total carry, all lanes
-    const int4 w = wsum[lane];
-    int4 wi = w;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    const int w = wsum[lane];
+    int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int4 t = shfl_up4(wi, o);
-      if (lane >= o) wi = add4(wi, t);
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
     }
-    wsum[lane] = make_int4(c.x + wi.x - w.x, c.y + wi.y - w.y, c.z + wi.z - w.z, c.w + wi.w - w.w);  // exclusive, incl. carry
+    wsum[lane] = c + wi - w;  // exclusive warp offset including the carry-in
   }
   __syncthreads();
-  const int4 wo = wsum[warp];
-  const int4 ex = make_int4(wo.x + inc.x - mine.x, wo.y + inc.y - mine.y, wo.z + inc.z - mine.z, wo.w + inc.w - mine.w);
-  if (v < p.V) {
-    p.off[v] = ex.x;
-    p.item_off[v] = ex.y;
-    p.hot_off[v] = ex.z;
-    p.pslot_off[v] = ex.w;
-  }
-  if (v == p.V - 1) {  // totals
-    p.off[p.V] = ex.x + mine.x;
-    p.item_off[p.V] = ex.y + mine.y;
-    p.hot_off[p.V] = ex.z + mine.z;
-    p.pslot_off[p.V] = ex.w + mine.w;
-  }
+  const int ex = wsum[warp] + inc - mine;
+  if (v < p.V) p.off[v] = ex;
+  if (v == p.V - 1) p.off[p.V] = ex + mine;
 }
 
-// threads [0, N): scatter positions into their token's segment (cursor = cnt, counted back down to 0);
-// threads [0, V): emit the work items of token v.
+// Scatter every position into its token's segment of the stream (cursor = cnt, counted back down to 0).
 __global__ void plan_fill_kernel(EmbedParams p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.N) {
     const int v = clampi(p.tok[i], p.V - 1);
     const int slot = atomicSub(&p.cnt[v], 1) - 1;
-    p.order[p.off[v] + slot] = (int)i;
-  }
-  if (i < p.V) {
-    const int v = (int)i;
-    const int start = p.off[v], c = p.off[v + 1] - start;
-    const int nch = (c + p.L - 1) / p.L;
-    const int ib = p.item_off[v];
-    const int ps = p.pslot_off[v];
-    for (int j = 0; j < nch; ++j)
-      p.items[ib + j] = make_int4(v, start + j * p.L, min(p.L, c - j * p.L), nch > 1 ? ps + j : -1);
-    if (nch > 1) p.hot_rows[p.hot_off[v]] = make_int4(v, ps, nch, 0);
+    const int at = p.off[v] + slot;
+    p.order[at] = (int)i;
+    p.stok[at] = v;
   }
 }
-
 
 __global__ void mot_lam_store_kernel(const float* __restrict__ acc, float* __restrict__ g_lam) {
   if (threadIdx.x < 2) g_lam[threadIdx.x] = acc[threadIdx.x];
@@ -157,25 +120,23 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.ttb_dtype = d->ttb_dtype;
   p.n_chunks = d->out_dim / kChunk;
   p.eps = d->eps;
-  // occurrences per work item: large enough that hot-row partials stay a few MB, small enough that one
-  // item is a short tail
-  long long L = 16;
-  while (L < 256 && d->n_tokens / L > 4096) L <<= 1;
-  p.L = (int)L;
+  // stream chunk size: 32 entries, grown so that there are at most ~4096 chunks (bounds the partial-row scratch)
+  long long R = 32;
+  while (d->n_tokens / R > 4096) R <<= 1;
+  p.R = (int)R;
+  p.n_rep = 16;
+  p.stages = 4;
+  p.tab_smem = 1;
 }
 
 struct WsLayout {
-  size_t cnt, off, item_off, hot_off, pslot_off, order, items, hot_rows, partial, byte_acc, lam_acc, total;
-  long long max_items, max_hot, max_pslots;
+  size_t cnt, byte_acc, lam_acc, zero_end, off, order, stok, partial, total;
 };
 
 static WsLayout ws_layout(const EmbedParams& p) {
   WsLayout w{};
   const long long V = p.V > 0 ? p.V : 1, N = p.N > 0 ? p.N : 1;
-  const long long chunks = N / p.L + 1;
-  w.max_hot = chunks < V ? chunks : V;
-  w.max_pslots = chunks + w.max_hot;
-  w.max_items = (N < V ? N : V) + chunks;
+  const long long n_stream_chunks = (N + p.R - 1) / p.R;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -184,16 +145,13 @@ static WsLayout ws_layout(const EmbedParams& p) {
   };
   // zeroed region first: cnt | byte_acc | lam_acc (one memset)
   w.cnt = take((size_t)V * 4);
-  w.byte_acc = take((size_t)(p.Vb > 0 ? p.Vb : 1) * p.bd * 4);
+  w.byte_acc = take((size_t)p.n_rep * (p.Vb > 0 ? p.Vb : 1) * p.bd * 4);
   w.lam_acc = take(16);
+  w.zero_end = o;
   w.off = take((size_t)(V + 1) * 4);
-  w.item_off = take((size_t)(V + 1) * 4);
-  w.hot_off = take((size_t)(V + 1) * 4);
-  w.pslot_off = take((size_t)(V + 1) * 4);
   w.order = take((size_t)N * 4);
-  w.items = take((size_t)w.max_items * 16);
-  w.hot_rows = take((size_t)w.max_hot * 16);
-  w.partial = take((size_t)w.max_pslots * (p.Dt > 0 ? p.Dt : 8) * 4);
+  w.stok = take((size_t)N * 4);
+  w.partial = take((size_t)2 * n_stream_chunks * (p.Dt > 0 ? p.Dt : 8) * 4);
   w.total = o;
   return w;
 }
@@ -204,12 +162,8 @@ static void bind_ws(EmbedParams& p, const WsLayout& w, void* ws) {
   p.byte_acc = reinterpret_cast<float*>(b + w.byte_acc);
   p.lam_acc = reinterpret_cast<float*>(b + w.lam_acc);
   p.off = reinterpret_cast<int*>(b + w.off);
-  p.item_off = reinterpret_cast<int*>(b + w.item_off);
-  p.hot_off = reinterpret_cast<int*>(b + w.hot_off);
-  p.pslot_off = reinterpret_cast<int*>(b + w.pslot_off);
   p.order = reinterpret_cast<int*>(b + w.order);
-  p.items = reinterpret_cast<int4*>(b + w.items);
-  p.hot_rows = reinterpret_cast<int4*>(b + w.hot_rows);
+  p.stok = reinterpret_cast<int*>(b + w.stok);
   p.partial = reinterpret_cast<float*>(b + w.partial);
 }
 
@@ -219,8 +173,7 @@ static int run_plan(const EmbedParams& p, cudaStream_t s) {
   if (hb > 2048) hb = 2048;
   plan_hist_kernel<<<(unsigned)hb, 256, 0, s>>>(p.tok, p.N, p.V, p.cnt);
   plan_scan_kernel<<<(unsigned)((p.V + 1023) / 1024), 1024, 0, s>>>(p);
-  const long long m = p.N > p.V ? p.N : p.V;
-  plan_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(p);
+  plan_fill_kernel<<<(unsigned)((p.N + 255) / 256), 256, 0, s>>>(p);
   count_launch(3);
   return check_launch();
 }
@@ -268,7 +221,7 @@ extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* worksp
   p.tok = tok;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // zero cnt | byte_acc | lam_acc (contiguous at the head of the workspace)
-  if (cudaMemsetAsync(workspace, 0, w.off, s) != cudaSuccess) return check_launch();
+  if (cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
   return run_plan(p, s);
 }
 
@@ -310,10 +263,10 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
   if (!plan_ready) {
-    if (cudaMemsetAsync(workspace, 0, w.off, s) != cudaSuccess) return check_launch();
+    if (cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
     if (int rc = run_plan(p, s)) return rc;
   } else {  // plan kept from mot_embed_plan(): only the accumulators need clearing
-    if (cudaMemsetAsync(reinterpret_cast<char*>(workspace) + w.byte_acc, 0, w.off - w.byte_acc, s) != cudaSuccess)
+    if (cudaMemsetAsync(reinterpret_cast<char*>(workspace) + w.byte_acc, 0, w.zero_end - w.byte_acc, s) != cudaSuccess)
       return check_launch();
   }
   int rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);

@@ -4,11 +4,12 @@ namespace mot {
 int dispatch_bwd_wide_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s) {
   using T = float;
-  switch ((p.n_chunks + 31) / 32) {
-    case 1: return launch_bwd<T, 1>(p, s);
-    case 2: return launch_bwd<T, 2>(p, s);
-    case 3: return launch_bwd<T, 3>(p, s);
-    case 4: return launch_bwd<T, 4>(p, s);
+  const int cpl = (p.n_chunks + 31) / 32;
+  switch (cpl) {
+    case 1: return launch_bwd<T, 1, 0>(p, s);
+    case 2: return launch_bwd<T, 2, 0>(p, s);
+    case 3: return launch_bwd<T, 3, 0>(p, s);
+    case 4: return launch_bwd<T, 4, 0>(p, s);
     default: return dispatch_bwd_wide_f32(p, s);
   }
 }

@@ -4,8 +4,8 @@ namespace mot {
 int dispatch_bwd_wide_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
   switch ((p.n_chunks + 31) / 32) {
-    case 5: case 6: return launch_bwd<T, 6>(p, s);
-    case 7: case 8: return launch_bwd<T, 8>(p, s);
+    case 5: case 6: return launch_bwd<T, 6, 0>(p, s);
+    case 7: case 8: return launch_bwd<T, 8, 0>(p, s);
   }
   return MOT_ERR_UNSUPPORTED;
 }

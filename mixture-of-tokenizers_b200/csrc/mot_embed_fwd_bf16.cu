@@ -3,13 +3,18 @@
 namespace mot {
 int dispatch_fwd_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
-  switch ((p.n_chunks + 31) / 32) {
-    case 1: return launch_fwd<T, 1>(p, s);
-    case 2: return launch_fwd<T, 2>(p, s);
-    case 3: return launch_fwd<T, 3>(p, s);
-    case 4: return launch_fwd<T, 4>(p, s);
-    case 5: case 6: return launch_fwd<T, 6>(p, s);
-    case 7: case 8: return launch_fwd<T, 8>(p, s);
+  const int cpl = (p.n_chunks + 31) / 32;
+  if (pick_mode(p) == 1) {  // MoT-sum fast path (runs/71), the shapes the reference ships
+    if (cpl == 3) return launch_fwd<T, 3, 1>(p, s);
+    if (cpl == 4) return launch_fwd<T, 4, 1>(p, s);
+  }
+  switch (cpl) {
+    case 1: return launch_fwd<T, 1, 0>(p, s);
+    case 2: return launch_fwd<T, 2, 0>(p, s);
+    case 3: return launch_fwd<T, 3, 0>(p, s);
+    case 4: return launch_fwd<T, 4, 0>(p, s);
+    case 5: case 6: return launch_fwd<T, 6, 0>(p, s);
+    case 7: case 8: return launch_fwd<T, 8, 0>(p, s);
   }
   return MOT_ERR_UNSUPPORTED;
 }

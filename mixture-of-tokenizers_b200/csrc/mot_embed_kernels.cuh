@@ -10,18 +10,23 @@
 // (bf16 or fp32); token ids int32 [N]; byte ids int32/int64, token-major [N,bpt] or slot-major [bpt,N];
 // ttb table [V,bpt] int16 (or the reference's fp32 / bf16 float containers).
 //
-// One warp owns one position (forward) or one token row with its occurrences (backward); a lane owns
-// chunks of 8 consecutive elements: chunk c = it*32 + lane, so a warp-wide access is one contiguous
-// 512 B (bf16) segment per `it`.  The byte table lives in shared memory (staged once per CTA with a
-// bulk async copy), so the only HBM streams are token rows, grad rows, output rows and the dense grad.
+// Execution model (both kernels): persistent CTAs, one per SM.  A warp owns one position (forward) or
+// one occurrence of the token-sorted stream (backward) at a time; a lane owns chunks of 8 consecutive
+// elements (chunk c = it*32 + lane -> every warp-wide access is a contiguous 512 B segment).  The rows
+// a warp needs next (token row; grad row + token row) are fetched by ONE lane with 1-D bulk async copies
+// (cp.async.bulk, the TMA engine) into a per-warp ring of shared-memory stages guarded by mbarriers, so
+// several KB per warp are in flight without holding registers.  The byte table (<= 117 KB) is staged in
+// shared memory once per CTA the same way.  HBM streams: token rows, grad rows, output rows, dense grad.
 #pragma once
 #include <cstdlib>
+
 #include "mot_common.cuh"
 
 namespace mot {
 
 constexpr int kFwdThreads = 512;
 constexpr int kBwdThreads = 384;
+constexpr int kMaxStages = 8;
 
 struct EmbedParams {
   const int32_t* tok;
@@ -37,22 +42,19 @@ struct EmbedParams {
   void* gE_byte;
   float* g_lam;
   // plan / workspace views
-  int* cnt;            // [V]     histogram, doubles as fill cursor
-  int* off;            // [V+1]   exclusive scan of cnt
-  int* item_off;       // [V+1]   exclusive scan of ceil(cnt/L)
-  int* hot_off;        // [V+1]   exclusive scan of [cnt > L]
-  int* pslot_off;      // [V+1]   exclusive scan of [cnt > L] * ceil(cnt/L)
-  int* order;          // [N]     positions grouped by token id
-  int4* items;         // [max_items]  {v, start, cnt, partial slot or -1}
-  int4* hot_rows;      // [max_hot]    {v, first partial slot, n chunks, 0}
-  float* partial;      // [max_pslots, Dt] fp32 partial sums of hot rows
-  float* byte_acc;     // [Vb*bd] fp32
-  float* lam_acc;      // [2]
+  int* cnt;         // [V]     histogram, doubles as fill cursor
+  int* off;         // [V+1]   exclusive scan of cnt
+  int* order;       // [N]     positions grouped by token id (the token-sorted stream)
+  int* stok;        // [N]     token id of every stream entry
+  float* partial;   // [2*n_stream_chunks, Dt] fp32 partial row sums (rows that straddle a chunk boundary)
+  float* byte_acc;  // [n_rep, Vb*bd] fp32, zeroed per call
+  float* lam_acc;   // [2]
   long long N, T;
   int V, Vb, bpt, Dt, bd, Do, combine, flags, ttb_dtype;
   int n_chunks;  // Do / 8
-  int L;         // occurrences per work item
-  int acc_stride;  // floats per row of the shared-memory accumulators (bd + 2: spreads rows over banks)
+  int R;         // stream entries per chunk (multiple of 32)
+  int n_rep;     // replicas of the byte-grad accumulator (spreads hot byte ids over L2 atomic units)
+  int stages;    // ring depth per warp
   int tab_smem;  // 1: byte table staged in shared memory; 0: too large, rows read through L1/L2
   float eps;
 };
@@ -129,22 +131,36 @@ __device__ __forceinline__ int fetch_id(const EmbedParams& p, long long pos, int
   return clampi(id, p.Vb - 1);
 }
 
-// Stage E_byte into shared memory with one bulk async copy per 32 KB and compute the per-row
-// rms scale (byte_norm).  rs[r] = rsqrt(mean(row^2) + eps) or 1.
+// Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all
+// variants); MODE 1: the MoT-sum fast path (runs/71): combine == ADD, out_norm only, no lambdas.
+template <int MODE>
+struct Cfg {
+  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 0 && (p.flags & MOT_F_TOK_NORM); }
+  __device__ __forceinline__ static bool byte_scale(const EmbedParams& p) {
+    return MODE == 0 && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN);
+  }
+  __device__ __forceinline__ static bool has_lam(const EmbedParams& p) { return MODE == 0 && (p.flags & MOT_F_HAS_LAMBDAS); }
+  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (p.flags & MOT_F_OUT_NORM); }
+  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || p.combine != MOT_BYTES_ONLY; }
+  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || p.combine != MOT_TOK_ONLY; }
+  __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MODE == 0 && p.combine == MOT_MEAN; }
+};
+inline int pick_mode(const EmbedParams& p) {
+  const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
+  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM) ? 1 : 0;
+}
+
 template <typename T>
 __device__ __forceinline__ typename Vec8<T>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
   return p.tab_smem ? Vec8<T>::lds_raw(tab + off) : Vec8<T>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
+// Stage E_byte into shared memory (bulk async copies of <= 32 KB) and compute the per-row rms scale
+// of byte_norm: rs[r] = rsqrt(mean(row^2) + eps), or 1.  Ends with __syncthreads().
 template <typename T>
 __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar) {
   if (p.tab_smem) {
     const uint32_t bytes = (uint32_t)p.Vb * p.bd * sizeof(T);
-    if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, bytes);
       for (uint32_t done = 0; done < bytes;) {
@@ -173,99 +189,126 @@ __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64
   __syncthreads();
 }
 
-// acc[0..8) += v[0..8).  Shared memory has no native fp32 atomic add (atomicAdd lowers to one
-// load + CAS spin loop PER element, 24 serial round trips per occurrence); here the four 64-bit words
-// are read once, the four CAS are issued back to back and only the losers retry.
-__device__ __forceinline__ void smem_add8(float* a, const float (&v)[8]) {
-  unsigned long long* a2 = reinterpret_cast<unsigned long long*>(a);
-  unsigned long long old[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) old[q] = *reinterpret_cast<volatile unsigned long long*>(a2 + q);
-  unsigned pending = 0xFu;
-  while (pending) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (pending & (1u << q)) {
-        const float lo = __uint_as_float((unsigned)old[q]) + v[2 * q];
-        const float hi = __uint_as_float((unsigned)(old[q] >> 32)) + v[2 * q + 1];
-        const unsigned long long nw = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
-        const unsigned long long prev = atomicCAS(a2 + q, old[q], nw);
-        if (prev == old[q]) pending &= ~(1u << q);
-        else old[q] = prev;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
-  atomicAdd(reinterpret_cast<float4*>(a), make_float4(v[0], v[1], v[2], v[3]));      // RED.E.ADD.F32x4
-  atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(v[4], v[5], v[6], v[7]));
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Shared-memory layout shared by both kernels:
+//   [rs: Vb floats][byte table (if tab_smem)][ring barriers: warps*stages u64][ring: warps*stages*stage_bytes]
+struct SmemLayout {
+  size_t rs, tab, bars, ring, stage_bytes, g_bytes, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(const EmbedParams& p, size_t esz, int warps, bool backward) {
+  SmemLayout L{};
+  const bool has_bytes = p.combine != MOT_TOK_ONLY, has_tok = p.combine != MOT_BYTES_ONLY;
+  size_t o = 0;
+  L.rs = o;
+  o += has_bytes ? align_up((size_t)p.Vb * 4, 128) : 0;
+  L.tab = o;
+  o += (has_bytes && p.tab_smem) ? align_up((size_t)p.Vb * p.bd * esz, 128) : 0;
+  L.bars = o;
+  o += align_up((size_t)warps * p.stages * 8, 128);
+  L.ring = o;
+  L.g_bytes = backward ? align_up((size_t)p.Do * esz, 128) : 0;
+  L.stage_bytes = L.g_bytes + (has_tok ? align_up((size_t)p.Dt * esz, 128) : 0);
+  o += (size_t)warps * p.stages * L.stage_bytes;
+  L.total = o;
+  return L;
 }
 
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// fp32 accumulate of 8 consecutive values into the L2-resident scratch: two RED.E.ADD.F32x4 (no return value,
+// no dependency chain).  Shared-memory fp32 atomics would be CAS spin loops (measured 1.4x slower end to end).
+__device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
+  atomicAdd(reinterpret_cast<float4*>(a), make_float4(v[0], v[1], v[2], v[3]));
+  atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
 
 // ======================================================================================
 // Forward
 // ======================================================================================
-template <typename T, int CPL>
-struct FwdLoad {
-  typename Vec8<T>::Raw traw[CPL];
-  int idreg;
-};
-
-template <typename T, int CPL>
-__global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams p) {
+template <typename T, int CPL, int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedParams p) {
+  using C = Cfg<MODE>;
+  using Raw = typename Vec8<T>::Raw;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
-  float* rs = reinterpret_cast<float*>(smem_raw);
-  T* tab = reinterpret_cast<T*>(smem_raw + align_up((size_t)p.Vb * sizeof(float), 128));
-  const bool has_tok = p.combine != MOT_BYTES_ONLY;
-  const bool has_bytes = p.combine != MOT_TOK_ONLY;
-  if (has_bytes) stage_byte_table<T>(p, tab, rs, &bar);
-
+  __shared__ uint64_t tab_bar;
   const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
-  const long long gw = (long long)blockIdx.x * nw + (threadIdx.x >> 5);
+  const SmemLayout L = smem_layout(p, sizeof(T), nw, false);
+  float* rs = reinterpret_cast<float*>(smem_raw + L.rs);
+  T* tab = reinterpret_cast<T*>(smem_raw + L.tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars) + warp * p.stages;
+  unsigned char* ring = smem_raw + L.ring + (size_t)warp * p.stages * L.stage_bytes;
+  const bool has_tok = C::has_tok(p), has_bytes = C::has_bytes(p);
+  const int D = p.stages;
+
+  if (threadIdx.x == 0) mbar_init(&tab_bar, 1);
+  if (lane == 0)
+    for (int s = 0; s < D; ++s) mbar_init(bars + s, 1);
+  fence_mbar_init();
+  __syncthreads();
+
+  const long long gw = (long long)blockIdx.x * nw + warp;
   const long long stride = (long long)gridDim.x * nw;
+  const long long n_i = gw < p.N ? (p.N - gw + stride - 1) / stride : 0;  // positions of this warp
+  const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
+  const uint32_t row_bytes = (uint32_t)p.Dt * sizeof(T);
+
+  // ring prologue first (so the token rows are in flight while the byte table is staged)
+  int tok_ahead = 0;  // lane 0: token id of position i + D
+  if (has_tok && lane == 0) {
+    for (int i = 0; i < D && i < n_i; ++i) {
+      const int tv = clampi(__ldg(p.tok + gw + i * stride), p.V - 1);
+      mbar_expect_tx(bars + i, row_bytes);
+      bulk_g2s(ring + (size_t)i * L.stage_bytes, E_tok + (size_t)tv * p.Dt, row_bytes, bars + i);
+    }
+    if (D < n_i) tok_ahead = clampi(__ldg(p.tok + gw + D * stride), p.V - 1);
+  }
+  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar);
 
   ChunkMap cm[CPL];
 #pragma unroll
   for (int it = 0; it < CPL; ++it) cm[it] = chunk_map(p, it * 32 + lane);
 
   float lam_t = 1.f, lam_b = 1.f;
-  if (p.flags & MOT_F_HAS_LAMBDAS) {
+  if (C::has_lam(p)) {
     lam_t = __ldg(p.lam);
     lam_b = __ldg(p.lam + 1);
   }
-  if (p.combine == MOT_MEAN) lam_b /= (float)p.bpt;
-  const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
+  if (C::mean(p)) lam_b /= (float)p.bpt;
   T* out = reinterpret_cast<T*>(p.out);
-  const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
-  const bool out_norm = (p.flags & MOT_F_OUT_NORM) != 0;
+  const bool tok_norm = C::tok_norm(p), out_norm = C::out_norm(p), byte_scale = C::byte_scale(p);
 
-  auto load = [&](long long pos, FwdLoad<T, CPL>& ld) {
-    ld.idreg = (has_bytes && lane < p.bpt) ? fetch_id(p, pos, lane) : 0;
-    if (has_tok) {
-      const int tv = clampi(__ldg(p.tok + pos), p.V - 1);
-      const T* row = E_tok + (size_t)tv * p.Dt;
-#pragma unroll
-      for (int it = 0; it < CPL; ++it)
-        if (cm[it].toff >= 0) ld.traw[it] = Vec8<T>::ldg_raw(row + cm[it].toff);
-    }
-  };
+  int id_next = (has_bytes && lane < p.bpt && n_i > 0) ? fetch_id(p, gw, lane) : 0;
+  for (long long i = 0; i < n_i; ++i) {
+    const long long pos = gw + i * stride;
+    const int s = (int)(i % D);
+    const uint32_t parity = (uint32_t)((i / D) & 1);
+    const int idreg = id_next;
+    if (has_bytes && lane < p.bpt && i + 1 < n_i) id_next = fetch_id(p, pos + stride, lane);
 
-  auto finish = [&](long long pos, FwdLoad<T, CPL>& ld) {
     float x[CPL][8];
     float ss_t = 0.f;
+    if (has_tok) {
+      mbar_wait(bars + s, parity);
+      const T* trow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes);
 #pragma unroll
-    for (int it = 0; it < CPL; ++it) {
-      if (cm[it].toff >= 0) {
-        Vec8<T>::unpack(ld.traw[it], x[it]);
+      for (int it = 0; it < CPL; ++it) {
+        if (cm[it].toff >= 0) {
+          Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), x[it]);
+          if (tok_norm) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ss_t += x[it][e] * x[it][e];
-      } else {
+            for (int e = 0; e < 8; ++e) ss_t += x[it][e] * x[it][e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < CPL; ++it)
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[it][e] = 0.f;
-      }
     }
     float tscale = lam_t;
     if (tok_norm) {
@@ -275,12 +318,14 @@ __global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams 
     float ss = 0.f;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
+      if (MODE == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[it][e] *= tscale;
+        for (int e = 0; e < 8; ++e) x[it][e] *= tscale;
+      }
       if (has_bytes) {
-        if (p.combine == MOT_MEAN) {
+        if (C::mean(p)) {
           for (int k = 0; k < p.bpt; ++k) {
-            const int id = __shfl_sync(0xffffffffu, ld.idreg, k);
+            const int id = __shfl_sync(0xffffffffu, idreg, k);
             if (cm[it].slot == -2) {
               float b[8];
               Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
@@ -290,67 +335,80 @@ __global__ void __launch_bounds__(kFwdThreads) mot_fwd_kernel(const EmbedParams 
             }
           }
         } else {
-          const int id = __shfl_sync(0xffffffffu, ld.idreg, cm[it].slot & 31);
+          const int id = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
           if (cm[it].slot >= 0) {
             float b[8];
             Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
-            const float bs = lam_b * rs[id];
+            if (byte_scale) {
+              const float bs = lam_b * rs[id];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
+              for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[it][e] += b[e];
+            }
           }
         }
       }
+      if (out_norm) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ss += x[it][e] * x[it][e];
+        for (int e = 0; e < 8; ++e) ss += x[it][e] * x[it][e];
+      }
     }
     float oscale = 1.f;
     if (out_norm) {
-      ss = warp_sum(ss);
+      ss = warp_sum(ss);  // every lane has consumed its shared-memory reads here: the stage can be refilled
       oscale = rsqrtf(ss / (float)p.Do + p.eps);
+    } else {
+      __syncwarp();
+    }
+    if (has_tok && lane == 0 && i + D < n_i) {
+      mbar_expect_tx(bars + s, row_bytes);
+      bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + (size_t)tok_ahead * p.Dt, row_bytes, bars + s);
+      if (i + D + 1 < n_i) tok_ahead = clampi(__ldg(p.tok + pos + (D + 1) * stride), p.V - 1);
     }
     T* orow = out + (size_t)pos * p.Do;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
       if (it * 32 + lane < p.n_chunks) {
+        if (out_norm) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[it][e] *= oscale;
+          for (int e = 0; e < 8; ++e) x[it][e] *= oscale;
+        }
         Vec8<T>::stg(orow + (size_t)(it * 32 + lane) * kChunk, x[it]);
       }
     }
-  };
-
-  for (long long pos = gw; pos < p.N; pos += 2 * stride) {
-    FwdLoad<T, CPL> a, b;
-    const bool two = pos + stride < p.N;  // warp-uniform
-    load(pos, a);
-    if (two) load(pos + stride, b);
-    finish(pos, a);
-    if (two) finish(pos + stride, b);
   }
 }
 
 // ======================================================================================
 // Backward
 // ======================================================================================
-// Finish one token row: given Du = sum over occurrences of d z[token part], the raw token row tv and
-// its rms scale r_t, write d E_tok[v] and return this row's contribution to d lam_tok.
-template <typename T, int CPL>
-__device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const ChunkMap (&cm)[CPL], int v,
-                                                float (&Du)[CPL][8], const typename Vec8<T>::Raw (&traw)[CPL],
-                                                float r_t, float lam_t) {
-  const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
-  float dot = 0.f;  // <Du, tv>
+// Finish one token row: Du = sum over its occurrences of d z[token part]; tv = the raw token row (shared or
+// global memory); writes d E_tok[v] and returns <Du, that> (the row's contribution to d lam_tok).
+template <typename T, int CPL, int MODE>
+__device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const ChunkMap (&cm)[CPL], int v, float (&Du)[CPL][8],
+                                                const T* trow_smem, float lam_t) {
+  using C = Cfg<MODE>;
+  const bool tok_norm = C::tok_norm(p);
+  const bool need_t = tok_norm || C::has_lam(p);
+  float dot = 0.f, ss = 0.f;  // <Du, tv>, |tv|^2
+  if (need_t) {
 #pragma unroll
-  for (int it = 0; it < CPL; ++it) {
-    if (cm[it].toff >= 0) {
-      float tv[8];
-      Vec8<T>::unpack(traw[it], tv);
+    for (int it = 0; it < CPL; ++it) {
+      if (cm[it].toff >= 0) {
+        float tv[8];
+        Vec8<T>::unpack(Vec8<T>::lds_raw(trow_smem + cm[it].toff), tv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dot += Du[it][e] * tv[e];
+        for (int e = 0; e < 8; ++e) {
+          dot += Du[it][e] * tv[e];
+          ss += tv[e] * tv[e];
+        }
+      }
     }
+    warp_sum2(dot, ss);
   }
-  const bool need_dot = tok_norm || (p.flags & MOT_F_HAS_LAMBDAS);
-  if (need_dot) dot = warp_sum(dot);
+  const float r_t = tok_norm ? rsqrtf(ss / (float)p.Dt + p.eps) : 1.f;
   // d that = lam_t * Du ; dt = r_t * d that - tv * r_t^3 * mean(d that . tv)
   const float a = lam_t * r_t;
   const float b = tok_norm ? lam_t * r_t * r_t * r_t * dot / (float)p.Dt : 0.f;
@@ -358,283 +416,357 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
 #pragma unroll
   for (int it = 0; it < CPL; ++it) {
     if (cm[it].toff >= 0) {
-      float tv[8], o[8];
-      Vec8<T>::unpack(traw[it], tv);
+      float o[8];
+      if (tok_norm) {
+        float tv[8];
+        Vec8<T>::unpack(Vec8<T>::lds_raw(trow_smem + cm[it].toff), tv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = a * Du[it][e] - b * tv[e];
+        for (int e = 0; e < 8; ++e) o[e] = a * Du[it][e] - b * tv[e];
+      } else if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = a * Du[it][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = Du[it][e];
+      }
       Vec8<T>::stg(grow + cm[it].toff, o);
     }
   }
-  return r_t * dot;  // <Du, that>
+  return r_t * dot;
 }
 
-template <typename T, int CPL, bool SMEM_ACC>
+template <typename T, int CPL, int MODE>
 __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedParams p) {
+  using C = Cfg<MODE>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
-  const size_t rs_bytes = align_up((size_t)p.Vb * sizeof(float), 128);
-  const size_t tab_bytes = p.tab_smem ? align_up((size_t)p.Vb * p.bd * sizeof(T), 128) : 0;
-  float* rs = reinterpret_cast<float*>(smem_raw);
-  T* tab = reinterpret_cast<T*>(smem_raw + rs_bytes);
-  float* acc = reinterpret_cast<float*>(smem_raw + rs_bytes + tab_bytes);
-  const bool has_tok = p.combine != MOT_BYTES_ONLY;
-  const bool has_bytes = p.combine != MOT_TOK_ONLY;
-  const int nacc = p.Vb * p.acc_stride;
-  if (has_bytes) {
-    if (SMEM_ACC)
-      for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0.f;
-    stage_byte_table<T>(p, tab, rs, &bar);  // ends with __syncthreads()
-  }
-  float* accp = SMEM_ACC ? acc : p.byte_acc;
-  const int astride = SMEM_ACC ? p.acc_stride : p.bd;
-
+  __shared__ uint64_t tab_bar;
   const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
-  const int gw = blockIdx.x * nw + (threadIdx.x >> 5);
+  const SmemLayout L = smem_layout(p, sizeof(T), nw, true);
+  float* rs = reinterpret_cast<float*>(smem_raw + L.rs);
+  T* tab = reinterpret_cast<T*>(smem_raw + L.tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars) + warp * p.stages;
+  unsigned char* ring = smem_raw + L.ring + (size_t)warp * p.stages * L.stage_bytes;
+  const bool has_tok = C::has_tok(p), has_bytes = C::has_bytes(p);
+  const int D = p.stages;
+
+  if (threadIdx.x == 0) mbar_init(&tab_bar, 1);
+  if (lane == 0)
+    for (int s = 0; s < D; ++s) mbar_init(bars + s, 1);
+  fence_mbar_init();
+  __syncthreads();
+
+  const int gw = blockIdx.x * nw + warp;
   const int W = gridDim.x * nw;
+  const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
+  const T* gout = reinterpret_cast<const T*>(p.gout);
+  const uint32_t g_bytes = (uint32_t)p.Do * sizeof(T);
+  const uint32_t t_bytes = has_tok ? (uint32_t)p.Dt * sizeof(T) : 0u;
+
+  // ---- the warp's share of the token-sorted stream: chunks gw, gw+W, ... of R entries, walked in
+  //      batches of 32 entries (one per lane) ----
+  const long long n_stream_chunks = (p.N + p.R - 1) / p.R;
+  const int bpc = p.R / 32;                                                     // batches per chunk
+  const long long my_chunks = gw < n_stream_chunks ? (n_stream_chunks - gw + W - 1) / W : 0;
+  const long long n_batches = my_chunks * bpc;
+  auto batch_start = [&](long long m) -> long long { return (gw + (m / bpc) * W) * (long long)p.R + (m % bpc) * 32; };
+  auto load_batch = [&](long long m, int& pos, int& v, int& cnt) {
+    pos = 0;
+    v = -1;
+    cnt = 0;
+    if (m >= n_batches) return;
+    const long long a = batch_start(m);
+    const long long left = p.N - a;
+    cnt = left <= 0 ? 0 : (left < 32 ? (int)left : 32);
+    if (lane < cnt) {
+      if (has_tok) {
+        pos = __ldg(p.order + a + lane);
+        v = __ldg(p.stok + a + lane);
+      } else {
+        pos = (int)(a + lane);  // bytes-only: no token table, the stream is the position order
+        v = 0;
+      }
+    }
+  };
+  int posA, vA, cntA, posB, vB, cntB;
+  load_batch(0, posA, vA, cntA);
+  load_batch(1, posB, vB, cntB);
+
+  // ---- ring: occurrence n of this warp lives in stage n % D ----
+  long long issued = 0, consumed = 0;
+  int iw = 0, ik = 0;  // issue cursor: batch (0 = A, 1 = B) and entry
+  auto try_issue = [&]() -> bool {
+    for (;;) {
+      const int cnt = iw ? cntB : cntA;
+      if (ik < cnt) break;
+      if (iw == 1) return false;  // ran past the prefetched batch: wait for the consumer to advance
+      iw = 1;
+      ik = 0;
+    }
+    const int pos = __shfl_sync(0xffffffffu, iw ? posB : posA, ik);
+    const int v = __shfl_sync(0xffffffffu, iw ? vB : vA, ik);
+    if (lane == 0) {
+      const int s = (int)(issued % D);
+      unsigned char* st = ring + (size_t)s * L.stage_bytes;
+      mbar_expect_tx(bars + s, g_bytes + t_bytes);
+      bulk_g2s(st, gout + (size_t)pos * p.Do, g_bytes, bars + s);
+      if (has_tok) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + s);
+    }
+    ++issued;
+    ++ik;
+    return true;
+  };
+  while (issued < D && try_issue()) {
+  }
+
+  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar);  // ring prologue already in flight
 
   ChunkMap cm[CPL];
 #pragma unroll
   for (int it = 0; it < CPL; ++it) cm[it] = chunk_map(p, it * 32 + lane);
 
-  const bool has_lam = (p.flags & MOT_F_HAS_LAMBDAS) != 0;
+  const bool has_lam = C::has_lam(p);
   float lam_t = 1.f, lam_b = 1.f;
   if (has_lam) {
     lam_t = __ldg(p.lam);
     lam_b = __ldg(p.lam + 1);
   }
-  const float inv_pool = (p.combine == MOT_MEAN) ? 1.f / (float)p.bpt : 1.f;
+  const float inv_pool = C::mean(p) ? 1.f / (float)p.bpt : 1.f;
   const float lam_b_eff = lam_b * inv_pool;
-  const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
-  const T* gout = reinterpret_cast<const T*>(p.gout);
-  const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
-  const bool out_norm = (p.flags & MOT_F_OUT_NORM) != 0;
+  const bool tok_norm = C::tok_norm(p), out_norm = C::out_norm(p), byte_scale = C::byte_scale(p);
   float dlam_t = 0.f, dlam_b = 0.f;  // per-lane partials
+  float* accp = p.byte_acc + (size_t)(gw % p.n_rep) * p.Vb * p.bd;
 
-  using Raw = typename Vec8<T>::Raw;
-  struct Occ {
-    Raw graw[CPL];
-    int idreg;
-  };
-  auto load_occ = [&](long long pos, Occ& o) {
-    o.idreg = (has_bytes && lane < p.bpt) ? fetch_id(p, pos, lane) : 0;
-    const T* grow = gout + (size_t)pos * p.Do;
-#pragma unroll
-    for (int it = 0; it < CPL; ++it)
-      if (it * 32 + lane < p.n_chunks) o.graw[it] = Vec8<T>::ldg_raw(grow + (size_t)(it * 32 + lane) * kChunk);
-  };
-
-  // z chunk of this occurrence: token part (tscale * tv) + byte part (lam_b * rs * row)
-  auto z_chunk = [&](int it, const Raw (&traw)[CPL], float tscale, int idreg, float (&z)[8], float (&bhat)[8]) {
-    if (cm[it].toff >= 0) {
-      Vec8<T>::unpack(traw[it], z);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) z[e] *= tscale;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) z[e] = 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bhat[e] = 0.f;
-    if (has_bytes) {
-      if (p.combine == MOT_MEAN) {
-        for (int k = 0; k < p.bpt; ++k) {
-          const int id = __shfl_sync(0xffffffffu, idreg, k);
-          if (cm[it].slot == -2) {
-            float b[8];
-            Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
-            const float r = rs[id];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bhat[e] += r * b[e];
-          }
-        }
-      } else {
-        const int id = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
-        if (cm[it].slot >= 0) {
-          float b[8];
-          Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
-          const float r = rs[id];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) bhat[e] = r * b[e];
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) z[e] += lam_b_eff * bhat[e];
-    }
-  };
-
-  // one occurrence: accumulates d z[token part] into Du and lam_b * d z[byte part] into the byte accumulators
-  auto process_occ = [&](const Occ& o, const Raw (&traw)[CPL], float tscale, float (&Du)[CPL][8]) {
-    float g[CPL][8];
-    float ss = 0.f, gz = 0.f;
-#pragma unroll
-    for (int it = 0; it < CPL; ++it) {
-      if (it * 32 + lane < p.n_chunks) {
-        Vec8<T>::unpack(o.graw[it], g[it]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[it][e] = 0.f;
-      }
-      if (out_norm) {
-        float z[8], bhat[8];
-        z_chunk(it, traw, tscale, o.idreg, z, bhat);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          ss += z[e] * z[e];
-          gz += g[it][e] * z[e];
-        }
-      }
-    }
-    float r_o = 1.f, coef = 0.f;
-    if (out_norm) {
-      warp_sum2(ss, gz);
-      r_o = rsqrtf(ss / (float)p.Do + p.eps);
-      coef = r_o * r_o * r_o * gz / (float)p.Do;
-    }
-#pragma unroll
-    for (int it = 0; it < CPL; ++it) {
-      float z[8], bhat[8];
-      z_chunk(it, traw, tscale, o.idreg, z, bhat);  // second pass: recompute instead of holding z in registers
-      float dz[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dz[e] = r_o * g[it][e] - coef * z[e];
-      if (cm[it].toff >= 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Du[it][e] += dz[e];
-      }
-      if (has_bytes) {
-        if (has_lam) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) dlam_b += inv_pool * dz[e] * bhat[e];
-        }
-        float bv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bv[e] = lam_b_eff * dz[e];
-        if (p.combine == MOT_MEAN) {
-          for (int k = 0; k < p.bpt; ++k) {
-            const int id = __shfl_sync(0xffffffffu, o.idreg, k);
-            if (cm[it].slot == -2) {
-              float* a = accp + (size_t)id * astride + cm[it].boff;
-              if (SMEM_ACC) smem_add8(a, bv); else gmem_add8(a, bv);
-            }
-          }
-        } else {
-          const int id = __shfl_sync(0xffffffffu, o.idreg, cm[it].slot & 31);
-          if (cm[it].slot >= 0) {
-            float* a = accp + (size_t)id * astride + cm[it].boff;
-            if (SMEM_ACC) smem_add8(a, bv); else gmem_add8(a, bv);
-          }
-        }
-      }
-    }
-  };
-
+  // ---- phase Z: rows nobody gathered get zeros (the dense-grad contract of the reference) ----
   if (has_tok) {
-    // ---- phase Z: rows nobody gathered get zeros (the dense-grad contract of the reference) ----
-    {
-      T* G = reinterpret_cast<T*>(p.gE_tok);
-      float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int vb = gw * 32; vb < p.V; vb += W * 32) {
-        const int v = vb + lane;
-        const bool empty = v < p.V && (p.off[v + 1] - p.off[v]) == 0;
-        unsigned m = __ballot_sync(0xffffffffu, empty);
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          T* row = G + (size_t)(vb + j) * p.Dt;
-          for (int c = lane; c < p.Dt / kChunk; c += 32) Vec8<T>::stg(row + c * kChunk, zero);
-        }
+    T* G = reinterpret_cast<T*>(p.gE_tok);
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int vb = gw * 32; vb < p.V; vb += W * 32) {
+      const int v = vb + lane;
+      const bool empty = v < p.V && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
+      unsigned m = __ballot_sync(0xffffffffu, empty);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        T* row = G + (size_t)(vb + j) * p.Dt;
+        for (int c = lane; c < p.Dt / kChunk; c += 32) Vec8<T>::stg(row + c * kChunk, zero);
       }
     }
-    // ---- phase I: work items = (token row, <= L occurrences) ----
-    const int n_items = p.item_off[p.V];
-    for (int j = gw; j < n_items; j += W) {
-      const int4 item = p.items[j];
-      const int v = item.x, start = item.y, cnt = item.z, pslot = item.w;
-      Raw traw[CPL];
-      const T* trow = E_tok + (size_t)v * p.Dt;
-      float ss_t = 0.f;
+  }
+
+  // ---- phase S: the stream ----
+  float Du[CPL][8];
+#pragma unroll
+  for (int it = 0; it < CPL; ++it)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
+  int cur_v = -1;
+  bool seg_lead = false;  // current row segment started at the chunk start and continues a row of the previous chunk
+  float tscale = lam_t;   // lam_t * r_t of the current row
+
+  // flush the current row segment: direct write if the whole row lies inside this chunk, else fp32 partial
+  auto flush = [&](long long chunk, bool trail) {
+    const T* trow = reinterpret_cast<const T*>(ring + (size_t)((consumed - 1) % D) * L.stage_bytes + L.g_bytes);
+    if (!seg_lead && !trail) {
+      const float d = finish_tok_row<T, CPL, MODE>(p, cm, cur_v, Du, trow, lam_t);
+      if (lane == 0) dlam_t += d;
+    } else {
+      float* prow = p.partial + (size_t)(2 * chunk + (seg_lead ? 0 : 1)) * p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (cm[it].toff >= 0) {
-          traw[it] = Vec8<T>::ldg_raw(trow + cm[it].toff);
-        } else {
-          traw[it] = Vec8<T>::zero_raw();
-        }
-      }
-      float r_t = 1.f;
-      if (tok_norm) {
-#pragma unroll
-        for (int it = 0; it < CPL; ++it) {
-          float tv[8];
-          Vec8<T>::unpack(traw[it], tv);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ss_t += tv[e] * tv[e];
-        }
-        ss_t = warp_sum(ss_t);
-        r_t = rsqrtf(ss_t / (float)p.Dt + p.eps);
-      }
-      const float tscale = lam_t * r_t;
-      float Du[CPL][8];
-#pragma unroll
-      for (int it = 0; it < CPL; ++it)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
-
-      for (int k0 = 0; k0 < cnt; k0 += 32) {
-        const int nb = min(32, cnt - k0);
-        const int mypos = (lane < nb) ? p.order[start + k0 + lane] : 0;
-        Occ cur, nxt;
-        load_occ(__shfl_sync(0xffffffffu, mypos, 0), cur);
-        for (int k = 0; k < nb; ++k) {
-          const bool more = k + 1 < nb;  // warp-uniform
-          if (more) load_occ(__shfl_sync(0xffffffffu, mypos, k + 1), nxt);
-          process_occ(cur, traw, tscale, Du);
-          if (more) cur = nxt;
-        }
-      }
-      if (pslot < 0) {
-        dlam_t += finish_tok_row<T, CPL>(p, cm, v, Du, traw, r_t, lam_t) * (lane == 0 ? 1.f : 0.f);
-      } else {
-        float* prow = p.partial + (size_t)pslot * p.Dt;
-#pragma unroll
-        for (int it = 0; it < CPL; ++it) {
-          if (cm[it].toff >= 0) {
-            *reinterpret_cast<float4*>(prow + cm[it].toff) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
-            *reinterpret_cast<float4*>(prow + cm[it].toff + 4) = make_float4(Du[it][4], Du[it][5], Du[it][6], Du[it][7]);
-          }
+          *reinterpret_cast<float4*>(prow + cm[it].toff) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
+          *reinterpret_cast<float4*>(prow + cm[it].toff + 4) = make_float4(Du[it][4], Du[it][5], Du[it][6], Du[it][7]);
         }
       }
     }
-  } else {
-    // bytes-only: no token table, plain position loop
-    Raw traw[CPL];
-#pragma unroll
-    for (int it = 0; it < CPL; ++it) traw[it] = Vec8<T>::zero_raw();
-    float Du[CPL][8];
 #pragma unroll
     for (int it = 0; it < CPL; ++it)
 #pragma unroll
       for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
-    for (long long pos = gw; pos < p.N; pos += W) {
-      Occ cur;
-      load_occ(pos, cur);
-      process_occ(cur, traw, 0.f, Du);
+  };
+
+  for (long long m = 0; m < n_batches; ++m) {
+    const long long chunk = gw + (m / bpc) * W;
+    const bool chunk_first = (m % bpc) == 0, chunk_last = (m % bpc) == bpc - 1;
+    const long long a = batch_start(m);
+    int v_before = -1;
+    if (has_tok && chunk_first && a > 0 && cntA > 0) v_before = __ldg(p.stok + a - 1);
+    const int pos_first = __shfl_sync(0xffffffffu, posA, 0);  // warp collective: outside lane-dependent branches
+    int id_next = (has_bytes && lane < p.bpt && cntA > 0) ? fetch_id(p, pos_first, lane) : 0;
+    for (int k = 0; k < cntA; ++k) {
+      const int pos = __shfl_sync(0xffffffffu, posA, k);
+      const int v = __shfl_sync(0xffffffffu, vA, k);
+      const bool new_row = has_tok && v != cur_v;
+      if (new_row) {  // flush BEFORE refilling the ring: the old row's token row sits in stage (consumed-1) % D
+        if (cur_v >= 0) flush(chunk, false);
+        seg_lead = chunk_first && k == 0 && v == v_before;
+        cur_v = v;
+      }
+      while (issued - consumed < D && try_issue()) {
+      }
+      const int idreg = id_next;
+      const int pos_ahead = __shfl_sync(0xffffffffu, posA, (k + 1) & 31);
+      if (has_bytes && lane < p.bpt && k + 1 < cntA) id_next = fetch_id(p, pos_ahead, lane);
+
+      const int s = (int)(consumed % D);
+      mbar_wait(bars + s, (uint32_t)((consumed / D) & 1));
+      ++consumed;
+      const T* grow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes);
+      const T* trow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes + L.g_bytes);
+
+      if (new_row && tok_norm) {
+        float ss_t = 0.f;
+#pragma unroll
+        for (int it = 0; it < CPL; ++it) {
+          if (cm[it].toff >= 0) {
+            float tv[8];
+            Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), tv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss_t += tv[e] * tv[e];
+          }
+        }
+        ss_t = warp_sum(ss_t);
+        tscale = lam_t * rsqrtf(ss_t / (float)p.Dt + p.eps);
+      }
+
+      int idv[CPL];  // byte id of this lane's slot per chunk (warp collective: outside lane-dependent branches)
+#pragma unroll
+      for (int it = 0; it < CPL; ++it) idv[it] = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
+      // z = tscale * t + lam_b * rs * b
+      float z[CPL][8];
+      float ss = 0.f, gz = 0.f;
+#pragma unroll
+      for (int it = 0; it < CPL; ++it) {
+        if (has_tok && cm[it].toff >= 0) {
+          Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), z[it]);
+          if (MODE == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) z[it][e] *= tscale;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[it][e] = 0.f;
+        }
+        if (has_bytes) {
+          if (C::mean(p)) {
+            for (int kk = 0; kk < p.bpt; ++kk) {
+              const int id = __shfl_sync(0xffffffffu, idreg, kk);
+              if (cm[it].slot == -2) {
+                float b[8];
+                Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                const float bs = lam_b_eff * rs[id];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z[it][e] += bs * b[e];
+              }
+            }
+          } else {
+            const int id = idv[it];
+            if (cm[it].slot >= 0) {
+              float b[8];
+              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              if (byte_scale) {
+                const float bs = lam_b_eff * rs[id];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z[it][e] += bs * b[e];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z[it][e] += b[e];
+              }
+            }
+          }
+        }
+        if (out_norm) {
+          if (it * 32 + lane < p.n_chunks) {
+            float g[8];
+            Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              ss += z[it][e] * z[it][e];
+              gz += g[e] * z[it][e];
+            }
+          }
+        }
+      }
+      float r_o = 1.f, coef = 0.f;
+      if (out_norm) {
+        warp_sum2(ss, gz);
+        r_o = rsqrtf(ss / (float)p.Do + p.eps);
+        coef = r_o * r_o * r_o * gz / (float)p.Do;
+      }
+#pragma unroll
+      for (int it = 0; it < CPL; ++it) {
+        const bool valid = it * 32 + lane < p.n_chunks;  // lane-dependent: no warp collectives under it
+        float dz[8];
+        if (valid) {
+          Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), dz);
+          if (out_norm) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dz[e] = r_o * dz[e] - coef * z[it][e];
+          }
+          if (cm[it].toff >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) Du[it][e] += dz[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dz[e] = 0.f;
+        }
+        if (has_bytes) {
+          if (C::mean(p)) {
+            for (int kk = 0; kk < p.bpt; ++kk) {
+              const int id = __shfl_sync(0xffffffffu, idreg, kk);
+              if (valid && cm[it].slot == -2) {
+                if (has_lam) {
+                  float b[8];
+                  Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                  const float r = rs[id] * inv_pool;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
+                }
+                float dzs[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dzs[e] = dz[e] * lam_b_eff;
+                gmem_add8(accp + (size_t)id * p.bd + cm[it].boff, dzs);
+              }
+            }
+          } else if (valid && cm[it].slot >= 0) {
+            const int id = idv[it];
+            if (has_lam) {  // d lam_byte += <dz, bhat>
+              float b[8];
+              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              const float r = rs[id];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
+            }
+            if (MODE == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dz[e] *= lam_b_eff;
+            }
+            gmem_add8(accp + (size_t)id * p.bd + cm[it].boff, dz);
+          }
+        }
+      }
+      __syncwarp();  // shared-memory reads of this stage are done (values consumed above)
     }
+    // end of batch: at the end of a chunk the open row segment is flushed
+    if (chunk_last || m + 1 == n_batches || cntB == 0) {
+      if (has_tok && cur_v >= 0) {
+        const long long b_end = chunk * (long long)p.R + p.R;
+        const bool trail = b_end < p.N && __ldg(p.stok + b_end) == cur_v;
+        flush(chunk, trail);
+        cur_v = -1;
+        seg_lead = false;
+      }
+    }
+    // advance: A <- B, prefetch the batch after
+    posA = posB; vA = vB; cntA = cntB;
+    if (iw == 1) iw = 0; else ik = 0;
+    load_batch(m + 2, posB, vB, cntB);
   }
 
-  // ---- CTA epilogue: flush the byte accumulators and the lambda partials ----
-  if (has_bytes && SMEM_ACC) {
-    __syncthreads();
-    const int c4 = p.bd / 4;  // float4 groups per row (bd is a multiple of 8)
-    for (int i = threadIdx.x; i < p.Vb * c4; i += blockDim.x) {
-      const int r = i / c4, c = (i - r * c4) * 4;
-      const float2 lo = *reinterpret_cast<const float2*>(acc + (size_t)r * p.acc_stride + c);
-      const float2 hi = *reinterpret_cast<const float2*>(acc + (size_t)r * p.acc_stride + c + 2);
-      if (lo.x != 0.f || lo.y != 0.f || hi.x != 0.f || hi.y != 0.f)
-        atomicAdd(reinterpret_cast<float4*>(p.byte_acc + (size_t)r * p.bd + c), make_float4(lo.x, lo.y, hi.x, hi.y));
-    }
-  }
+  // ---- lambda partials ----
   if (has_lam) {
     dlam_t = warp_sum(dlam_t);
     dlam_b = warp_sum(dlam_b);
@@ -645,8 +777,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   }
 }
 
-// Finalize: (a) hot token rows: sum their fp32 partials in order, apply the token-norm backward, write
-// the row; (b) byte table: apply the byte-norm backward to the accumulated rows and cast; (c) lambdas.
+// Finalize: (a) token rows that straddle stream-chunk boundaries: sum their fp32 partials in stream order,
+// apply the token-norm backward, write the row; (b) byte table: sum the accumulator replicas, apply the
+// byte-norm backward, cast; (c) lambda partials of (a).
 template <typename T>
 __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams p) {
   const int lane = lane_id();
@@ -661,78 +794,96 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
   float dlam_t = 0.f;
   if (has_tok) {
     const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
-    const int n_hot = p.hot_off[p.V];
+    const long long n_stream_chunks = (p.N + p.R - 1) / p.R;
     const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
     T* G = reinterpret_cast<T*>(p.gE_tok);
-    for (int h = gw; h < n_hot; h += W) {
-      const int4 hr = p.hot_rows[h];
-      const int v = hr.x, ps = hr.y, nch = hr.z;
+    for (long long c0 = gw; c0 + 1 < n_stream_chunks; c0 += W) {
+      const long long bnd = (c0 + 1) * (long long)p.R;  // first stream entry of chunk c0 + 1
+      const int v = __ldg(p.stok + bnd - 1);
+      if (__ldg(p.stok + bnd) != v) continue;                  // no row crosses this boundary
+      const int o0 = __ldg(p.off + v), o1 = __ldg(p.off + v + 1);
+      if (o0 < c0 * (long long)p.R) continue;                  // the row started in an earlier chunk: not ours
+      const long long c1 = (o1 - 1) / p.R;                     // last chunk of the row
       const T* trow = E_tok + (size_t)v * p.Dt;
-      // pass 1: dot = <Du, tv>, ss = |tv|^2
       float dot = 0.f, ss = 0.f;
-      for (int c = lane; c < p.Dt / kChunk; c += 32) {
-        float tv[8], du[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
-        for (int j = 0; j < nch; ++j) {
-          const float* pr = p.partial + (size_t)(ps + j) * p.Dt + c * kChunk;
-          const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
-          du[0] += a.x; du[1] += a.y; du[2] += a.z; du[3] += a.w;
-          du[4] += b.x; du[5] += b.y; du[6] += b.z; du[7] += b.w;
-        }
+      for (int pass = 0; pass < 2; ++pass) {
+        const float r_t = tok_norm ? rsqrtf(ss / (float)p.Dt + p.eps) : 1.f;
+        const float a_ = lam_t * r_t;
+        const float b_ = tok_norm ? lam_t * r_t * r_t * r_t * dot / (float)p.Dt : 0.f;
+        float dacc = 0.f, sacc = 0.f;
+        for (int c = lane; c < p.Dt / kChunk; c += 32) {
+          float tv[8], du[8];
+          Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
+          {
+            const float* pr = p.partial + (size_t)(2 * c0 + 1) * p.Dt + c * kChunk;  // trailing partial of c0
+            const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
+            du[0] = x.x; du[1] = x.y; du[2] = x.z; du[3] = x.w; du[4] = y.x; du[5] = y.y; du[6] = y.z; du[7] = y.w;
+          }
+          for (long long cc = c0 + 1; cc <= c1; ++cc) {                                // leading partials
+            const float* pr = p.partial + (size_t)(2 * cc) * p.Dt + c * kChunk;
+            const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
+            du[0] += x.x; du[1] += x.y; du[2] += x.z; du[3] += x.w; du[4] += y.x; du[5] += y.y; du[6] += y.z; du[7] += y.w;
+          }
+          if (pass == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          dot += du[e] * tv[e];
-          ss += tv[e] * tv[e];
+            for (int e = 0; e < 8; ++e) {
+              dacc += du[e] * tv[e];
+              sacc += tv[e] * tv[e];
+            }
+          } else {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = a_ * du[e] - b_ * tv[e];
+            Vec8<T>::stg(G + (size_t)v * p.Dt + c * kChunk, o);
+          }
+        }
+        if (pass == 0) {
+          warp_sum2(dacc, sacc);
+          dot = dacc;
+          ss = sacc;
+          if (lane == 0) dlam_t += (tok_norm ? rsqrtf(ss / (float)p.Dt + p.eps) : 1.f) * dot;
         }
       }
-      warp_sum2(dot, ss);
-      const float r_t = tok_norm ? rsqrtf(ss / (float)p.Dt + p.eps) : 1.f;
-      const float a_ = lam_t * r_t;
-      const float b_ = tok_norm ? lam_t * r_t * r_t * r_t * dot / (float)p.Dt : 0.f;
-      for (int c = lane; c < p.Dt / kChunk; c += 32) {
-        float tv[8], du[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
-        Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
-        for (int j = 0; j < nch; ++j) {
-          const float* pr = p.partial + (size_t)(ps + j) * p.Dt + c * kChunk;
-          const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
-          du[0] += a.x; du[1] += a.y; du[2] += a.z; du[3] += a.w;
-          du[4] += b.x; du[5] += b.y; du[6] += b.z; du[7] += b.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = a_ * du[e] - b_ * tv[e];
-        Vec8<T>::stg(G + (size_t)v * p.Dt + c * kChunk, o);
-      }
-      if (lane == 0) dlam_t += r_t * dot;
     }
   }
   if (has_bytes) {
     const bool bn = (p.flags & MOT_F_BYTE_NORM) != 0;
     const T* E_byte = reinterpret_cast<const T*>(p.E_byte);
     T* G = reinterpret_cast<T*>(p.gE_byte);
+    const size_t rep_stride = (size_t)p.Vb * p.bd;
     for (int r = gw; r < p.Vb; r += W) {
       float dot = 0.f, ss = 0.f;
-      if (bn) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const float rsr = bn ? rsqrtf(ss / (float)p.bd + p.eps) : 1.f;
+        const float b_ = bn ? rsr * rsr * rsr * dot / (float)p.bd : 0.f;
+        float dacc = 0.f, sacc = 0.f;
+        if (pass == 0 && !bn) continue;
         for (int c = lane; c < p.bd / kChunk; c += 32) {
-          float ev[8];
+          float ev[8], a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
-          const float* a = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+          for (int rep = 0; rep < p.n_rep; ++rep) {
+            const float* src = p.byte_acc + rep * rep_stride + (size_t)r * p.bd + c * kChunk;
+            const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
+            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w; a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
+          }
+          if (pass == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            dot += a[e] * ev[e];
-            ss += ev[e] * ev[e];
+            for (int e = 0; e < 8; ++e) {
+              dacc += a[e] * ev[e];
+              sacc += ev[e] * ev[e];
+            }
+          } else {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = rsr * a[e] - b_ * ev[e];
+            Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, o);
           }
         }
-        warp_sum2(dot, ss);
-      }
-      const float rsr = bn ? rsqrtf(ss / (float)p.bd + p.eps) : 1.f;
-      const float b_ = bn ? rsr * rsr * rsr * dot / (float)p.bd : 0.f;
-      for (int c = lane; c < p.bd / kChunk; c += 32) {
-        float ev[8], o[8];
-        Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
-        const float* a = p.byte_acc + (size_t)r * p.bd + c * kChunk;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rsr * a[e] - b_ * ev[e];
-        Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, o);
+        if (pass == 0) {
+          warp_sum2(dacc, sacc);
+          dot = dacc;
+          ss = sacc;
+        }
       }
     }
   }
@@ -742,34 +893,36 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
   }
 }
 
-
-inline size_t smem_bytes(const EmbedParams& p, size_t esz, bool tab, bool acc) {
-  if (p.combine == MOT_TOK_ONLY) return 0;
-  return align_up((size_t)p.Vb * 4, 128) + (tab ? align_up((size_t)p.Vb * p.bd * esz, 128) : 0) +
-         (acc ? align_up((size_t)p.Vb * (p.bd + 2) * 4, 128) : 0);
+// ======================================================================================
+// Launchers
+// ======================================================================================
+// Pick the ring depth and whether the byte table fits next to it; returns dynamic smem bytes or 0.
+inline size_t plan_smem(EmbedParams& p, size_t esz, int warps, bool backward, int optin) {
+  const int want = backward ? 4 : 4;
+  p.tab_smem = 1;
+  for (int tab = 1; tab >= 0; --tab) {
+    p.tab_smem = tab;
+    for (int st = want; st >= 2; --st) {
+      p.stages = st;
+      const SmemLayout L = smem_layout(p, esz, warps, backward);
+      if (L.total + 1024 <= (size_t)optin) return L.total;
+    }
+  }
+  return 0;
 }
 
-template <typename T, int CPL>
+template <typename T, int CPL, int MODE>
 static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
-  p.tab_smem = 1;
-  size_t smem = smem_bytes(p, sizeof(T), true, false);
-  if (smem + 1024 > (size_t)optin) {  // table larger than one SM's shared memory: gather rows through L1/L2
-    p.tab_smem = 0;
-    smem = smem_bytes(p, sizeof(T), false, false);
-  }
-  auto kern = mot_fwd_kernel<T, CPL>;
+  const size_t smem = plan_smem(p, sizeof(T), kFwdThreads / 32, false, optin);
+  if (smem == 0) return MOT_ERR_UNSUPPORTED;
+  auto kern = mot_fwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFwdThreads, smem);
-  if (occ < 1) occ = 1;
-  const long long warps_needed = (p.N + 1) / 2;  // two positions per warp iteration
+  const long long warps_needed = p.N;
   long long blocks = (warps_needed + (kFwdThreads / 32) - 1) / (kFwdThreads / 32);
-  const long long cap = (long long)sms * occ;
-  if (blocks > cap) blocks = cap;
+  if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   if (g_prof_fwd_start) cudaEventRecord(g_prof_fwd_start, s);
   kern<<<(unsigned)blocks, kFwdThreads, smem, s>>>(p);
@@ -778,42 +931,21 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   return check_launch();
 }
 
-
-template <typename T, int CPL>
+template <typename T, int CPL, int MODE>
 static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
-  // preference: table + fp32 accumulators in shared memory; else accumulators in the L2-resident
-  // scratch (fp32 atomics); else the table through L1/L2 as well
-  bool smem_acc = true;
-  p.tab_smem = 1;
-  p.acc_stride = p.bd + 2;
-  static const char* acc_env = getenv("MOT_BWD_ACC");  // debug knob: "global" forces the L2-atomics path
-  const bool force_global = acc_env && acc_env[0] == 'g';
-  size_t smem = smem_bytes(p, sizeof(T), true, true);
-  if (force_global || smem + 1024 > (size_t)optin) {
-    smem_acc = false;
-    smem = smem_bytes(p, sizeof(T), true, false);
-    if (smem + 1024 > (size_t)optin) {
-      p.tab_smem = 0;
-      smem = smem_bytes(p, sizeof(T), false, false);
-    }
-  }
-  auto kern = smem_acc ? mot_bwd_kernel<T, CPL, true> : mot_bwd_kernel<T, CPL, false>;
+  const size_t smem = plan_smem(p, sizeof(T), kBwdThreads / 32, true, optin);
+  if (smem == 0) return MOT_ERR_UNSUPPORTED;
+  auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBwdThreads, smem);
-  if (occ < 1) occ = 1;
-  long long blocks = (long long)sms * occ;
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
-  kern<<<(unsigned)blocks, kBwdThreads, smem, s>>>(p);
+  kern<<<(unsigned)sms, kBwdThreads, smem, s>>>(p);
   if (g_prof_stop) cudaEventRecord(g_prof_stop, s);
   count_launch();
   return check_launch();
 }
-
-
 
 // per-translation-unit dispatchers (one TU per element type so nvcc compiles them in parallel)
 int dispatch_fwd_bf16(const EmbedParams& p, cudaStream_t s);
