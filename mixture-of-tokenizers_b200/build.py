@@ -23,7 +23,7 @@ OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-DNDEBUG",
+    "-O3", "-lineinfo", "-std=c++17", "-DNDEBUG", *(["-DMOT_EXPERIMENT_NO_RED"] if os.environ.get("MOT_EXPERIMENT_NO_RED") else []),
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]

@@ -85,6 +85,7 @@ static int validate(const MotDesc* d) {
   if (has_bytes) {
     if (d->byte_vocab <= 0 || d->byte_dim <= 0 || d->bpt <= 0 || d->bpt > 32) return MOT_ERR_BAD_ARG;
     if (d->byte_dim % 8) return MOT_ERR_MISALIGNED;
+    if ((d->flags & MOT_F_BYTE_NORM) && d->byte_dim > 256) return MOT_ERR_UNSUPPORTED;
   }
   const long long db = (long long)d->bpt * d->byte_dim;
   switch (d->combine) {
@@ -124,7 +125,7 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   long long R = 32;
   while (d->n_tokens / R > 4096) R <<= 1;
   p.R = (int)R;
-  p.n_rep = 16;
+  p.n_rep = kByteRep;
   p.stages = 4;
   p.tab_smem = 1;
 }
@@ -273,7 +274,13 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
   if (rc) return rc;
   int sms = 0, optin = 0;
   device_props(&sms, &optin);
-  rc = d->dtype == MOT_BF16 ? launch_finalize_bf16(p, sms, s) : launch_finalize_f32(p, sms, s);
+  {  // one warp per task (chunk boundary or byte row), 8 warps per CTA
+    const long long tasks = (has_tok ? (p.N + p.R - 1) / p.R : 0) + p.Vb;
+    long long fb = (tasks + 7) / 8;
+    if (fb > 8LL * sms) fb = 8LL * sms;
+    if (fb < 1) fb = 1;
+    rc = d->dtype == MOT_BF16 ? launch_finalize_bf16(p, (int)fb, s) : launch_finalize_f32(p, (int)fb, s);
+  }
   if (rc) return rc;
   if ((d->flags & MOT_F_HAS_LAMBDAS) && g_lam) {
     mot_lam_store_kernel<<<1, 32, 0, s>>>(p.lam_acc, g_lam);

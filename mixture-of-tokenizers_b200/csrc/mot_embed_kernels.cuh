@@ -24,9 +24,10 @@
 
 namespace mot {
 
-constexpr int kFwdThreads = 512;
+constexpr int kFwdThreads = 1024;
 constexpr int kBwdThreads = 384;
 constexpr int kMaxStages = 8;
+constexpr int kByteRep = 16;  // replicas of the fp32 byte-grad accumulator (spreads hot byte ids over L2 atomic units)
 
 struct EmbedParams {
   const int32_t* tok;
@@ -106,7 +107,9 @@ __device__ __forceinline__ ChunkMap chunk_map(const EmbedParams& p, int c) {
 
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
 
-// byte id of (position, slot); slot < bpt.  Out-of-range ids are clamped (the reference device-asserts).
+// RAW byte id of (position, slot); slot < bpt.  The caller clamps it with clamp_id() where it is consumed,
+// one iteration later, so the load's latency is not exposed at the load site (the pipeline issues in order).
+// Out-of-range ids are clamped (the reference device-asserts).
 __device__ __forceinline__ int fetch_id(const EmbedParams& p, long long pos, int slot) {
   int id;
   if (p.flags & MOT_F_IDS_FROM_TTB) {
@@ -128,7 +131,29 @@ __device__ __forceinline__ int fetch_id(const EmbedParams& p, long long pos, int
     id = (p.flags & MOT_F_IDS_I64) ? (int)__ldg(reinterpret_cast<const long long*>(p.ids) + idx)
                                    : __ldg(reinterpret_cast<const int*>(p.ids) + idx);
   }
-  return clampi(id, p.Vb - 1);
+  return id;
+}
+__device__ __forceinline__ int clamp_id(const EmbedParams& p, int id) { return clampi(id, p.Vb - 1); }
+
+// Per-lane view of the byte-id source, set up once: one multiply-add + load per position.
+struct IdSrc {
+  const char* base;      // address of (position 0, slot = lane) for id tensors
+  long long pos_stride;  // bytes between consecutive positions
+  int kind;              // 0: int32 tensor, 1: int64 tensor, 2: derived from the ttb table
+};
+__device__ __forceinline__ IdSrc make_id_src(const EmbedParams& p, int slot) {
+  IdSrc s;
+  const int esz = (p.flags & MOT_F_IDS_I64) ? 8 : 4;
+  s.kind = (p.flags & MOT_F_IDS_FROM_TTB) ? 2 : ((p.flags & MOT_F_IDS_I64) ? 1 : 0);
+  const bool sm = (p.flags & MOT_F_SLOT_MAJOR) != 0;
+  s.base = reinterpret_cast<const char*>(p.ids) + (sm ? (long long)slot * p.N : (long long)slot) * esz;
+  s.pos_stride = (sm ? 1LL : (long long)p.bpt) * esz;
+  return s;
+}
+__device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s, int pos, int slot) {
+  if (s.kind == 2) return fetch_id(p, pos, slot);
+  const char* a = s.base + (long long)pos * s.pos_stride;
+  return s.kind == 1 ? (int)__ldg(reinterpret_cast<const long long*>(a)) : __ldg(reinterpret_cast<const int*>(a));
 }
 
 // Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all
@@ -147,11 +172,16 @@ struct Cfg {
 };
 inline int pick_mode(const EmbedParams& p) {
   const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
-  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM) ? 1 : 0;
+  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.n_chunks % 32 == 0 && p.tab_smem) ? 1 : 0;
 }
 
-template <typename T>
+#define MOT_TOK_OK(it) (MODE == 1 || cm[it].toff >= 0)
+#define MOT_BYTE_OK(it) (MODE == 1 || cm[it].slot >= 0)
+#define MOT_CHUNK_OK(it) (MODE == 1 || (it) * 32 + lane < p.n_chunks)
+
+template <typename T, int MODE = 0>
 __device__ __forceinline__ typename Vec8<T>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
+  if (MODE == 1) return Vec8<T>::lds_raw(tab + off);  // the fast path is only dispatched when the table fits
   return p.tab_smem ? Vec8<T>::lds_raw(tab + off) : Vec8<T>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
@@ -217,6 +247,10 @@ __host__ __device__ inline SmemLayout smem_layout(const EmbedParams& p, size_t e
 // fp32 accumulate of 8 consecutive values into the L2-resident scratch: two RED.E.ADD.F32x4 (no return value,
 // no dependency chain).  Shared-memory fp32 atomics would be CAS spin loops (measured 1.4x slower end to end).
 __device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
+#ifdef MOT_EXPERIMENT_NO_RED
+  if (v[0] == 12345.678f) a[0] = v[1];
+  return;
+#endif
   atomicAdd(reinterpret_cast<float4*>(a), make_float4(v[0], v[1], v[2], v[3]));
   atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
@@ -247,21 +281,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
   fence_mbar_init();
   __syncthreads();
 
-  const long long gw = (long long)blockIdx.x * nw + warp;
-  const long long stride = (long long)gridDim.x * nw;
-  const long long n_i = gw < p.N ? (p.N - gw + stride - 1) / stride : 0;  // positions of this warp
+  const int gw = blockIdx.x * nw + warp;   // n_tokens < 2^31 (validated on the host): 32-bit position math
+  const int stride = gridDim.x * nw;
+  const int Ni = (int)p.N;
+  const int n_i = gw < Ni ? (Ni - gw + stride - 1) / stride : 0;  // positions of this warp
   const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
   const uint32_t row_bytes = (uint32_t)p.Dt * sizeof(T);
 
   // ring prologue first (so the token rows are in flight while the byte table is staged)
-  int tok_ahead = 0;  // lane 0: token id of position i + D
+  int tok_ahead = 0;  // lane 0: raw token id of position i + D
   if (has_tok && lane == 0) {
     for (int i = 0; i < D && i < n_i; ++i) {
       const int tv = clampi(__ldg(p.tok + gw + i * stride), p.V - 1);
       mbar_expect_tx(bars + i, row_bytes);
       bulk_g2s(ring + (size_t)i * L.stage_bytes, E_tok + (size_t)tv * p.Dt, row_bytes, bars + i);
     }
-    if (D < n_i) tok_ahead = clampi(__ldg(p.tok + gw + D * stride), p.V - 1);
+    if (D < n_i) tok_ahead = __ldg(p.tok + gw + D * stride);  // raw; clamped where it is used
   }
   if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar);
 
@@ -278,13 +313,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
   T* out = reinterpret_cast<T*>(p.out);
   const bool tok_norm = C::tok_norm(p), out_norm = C::out_norm(p), byte_scale = C::byte_scale(p);
 
-  int id_next = (has_bytes && lane < p.bpt && n_i > 0) ? fetch_id(p, gw, lane) : 0;
-  for (long long i = 0; i < n_i; ++i) {
-    const long long pos = gw + i * stride;
-    const int s = (int)(i % D);
-    const uint32_t parity = (uint32_t)((i / D) & 1);
-    const int idreg = id_next;
-    if (has_bytes && lane < p.bpt && i + 1 < n_i) id_next = fetch_id(p, pos + stride, lane);
+  const float inv_Dt = 1.f / (float)(p.Dt > 0 ? p.Dt : 1), inv_Do = 1.f / (float)p.Do;
+  const bool id_lane = has_bytes && lane < p.bpt;
+  const IdSrc idsrc = make_id_src(p, lane);
+  // raw byte ids are fetched two positions ahead and clamped where they are consumed
+  int id_n1 = (id_lane && n_i > 0) ? load_raw_id(p, idsrc, gw, lane) : 0;
+  int id_n2 = (id_lane && n_i > 1) ? load_raw_id(p, idsrc, gw + stride, lane) : 0;
+  int s = 0;
+  uint32_t parity = 0;
+  int pos = gw;
+  for (int i = 0; i < n_i; ++i, pos += stride) {
+    const int idreg = clamp_id(p, id_n1);
+    id_n1 = id_n2;
+    if (id_lane && i + 2 < n_i) id_n2 = load_raw_id(p, idsrc, pos + 2 * stride, lane);
 
     float x[CPL][8];
     float ss_t = 0.f;
@@ -293,7 +334,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
       const T* trow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes);
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
-        if (cm[it].toff >= 0) {
+        if (MOT_TOK_OK(it)) {
           Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), x[it]);
           if (tok_norm) {
 #pragma unroll
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
     float tscale = lam_t;
     if (tok_norm) {
       ss_t = warp_sum(ss_t);
-      tscale *= rsqrtf(ss_t / (float)p.Dt + p.eps);
+      tscale *= rsqrtf(ss_t * inv_Dt + p.eps);
     }
     float ss = 0.f;
 #pragma unroll
@@ -328,7 +369,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
             const int id = __shfl_sync(0xffffffffu, idreg, k);
             if (cm[it].slot == -2) {
               float b[8];
-              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               const float bs = lam_b * rs[id];
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
@@ -336,9 +377,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
           }
         } else {
           const int id = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
-          if (cm[it].slot >= 0) {
+          if (MOT_BYTE_OK(it)) {
             float b[8];
-            Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+            Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
             if (byte_scale) {
               const float bs = lam_b * rs[id];
 #pragma unroll
@@ -358,19 +399,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
     float oscale = 1.f;
     if (out_norm) {
       ss = warp_sum(ss);  // every lane has consumed its shared-memory reads here: the stage can be refilled
-      oscale = rsqrtf(ss / (float)p.Do + p.eps);
+      oscale = rsqrtf(ss * inv_Do + p.eps);
     } else {
       __syncwarp();
     }
     if (has_tok && lane == 0 && i + D < n_i) {
       mbar_expect_tx(bars + s, row_bytes);
-      bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + (size_t)tok_ahead * p.Dt, row_bytes, bars + s);
-      if (i + D + 1 < n_i) tok_ahead = clampi(__ldg(p.tok + pos + (D + 1) * stride), p.V - 1);
+      bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + (size_t)clampi(tok_ahead, p.V - 1) * p.Dt, row_bytes, bars + s);
+      if (i + D + 1 < n_i) tok_ahead = __ldg(p.tok + pos + (D + 1) * stride);
+    }
+    if (++s == D) {
+      s = 0;
+      parity ^= 1u;
     }
     T* orow = out + (size_t)pos * p.Do;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
-      if (it * 32 + lane < p.n_chunks) {
+      if (MOT_CHUNK_OK(it)) {
         if (out_norm) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) x[it][e] *= oscale;
@@ -396,7 +441,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
   if (need_t) {
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
-      if (cm[it].toff >= 0) {
+      if (MOT_TOK_OK(it)) {
         float tv[8];
         Vec8<T>::unpack(Vec8<T>::lds_raw(trow_smem + cm[it].toff), tv);
 #pragma unroll
@@ -415,7 +460,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
   T* grow = reinterpret_cast<T*>(p.gE_tok) + (size_t)v * p.Dt;
 #pragma unroll
   for (int it = 0; it < CPL; ++it) {
-    if (cm[it].toff >= 0) {
+    if (MOT_TOK_OK(it)) {
       float o[8];
       if (tok_norm) {
         float tv[8];
@@ -466,19 +511,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 
   // ---- the warp's share of the token-sorted stream: chunks gw, gw+W, ... of R entries, walked in
   //      batches of 32 entries (one per lane) ----
-  const long long n_stream_chunks = (p.N + p.R - 1) / p.R;
-  const int bpc = p.R / 32;                                                     // batches per chunk
-  const long long my_chunks = gw < n_stream_chunks ? (n_stream_chunks - gw + W - 1) / W : 0;
-  const long long n_batches = my_chunks * bpc;
-  auto batch_start = [&](long long m) -> long long { return (gw + (m / bpc) * W) * (long long)p.R + (m % bpc) * 32; };
-  auto load_batch = [&](long long m, int& pos, int& v, int& cnt) {
+  const int Ni = (int)p.N;  // n_tokens < 2^31 (validated on the host): 32-bit stream math
+  const int n_stream_chunks = (Ni + p.R - 1) / p.R;
+  const int bpc = p.R / 32;  // batches per chunk
+  const int my_chunks = gw < n_stream_chunks ? (n_stream_chunks - gw + W - 1) / W : 0;
+  const int n_batches = my_chunks * bpc;
+  auto batch_start = [&](int m) -> int { return (gw + (m / bpc) * W) * p.R + (m % bpc) * 32; };
+  auto load_batch = [&](int m, int& pos, int& v, int& cnt) {
     pos = 0;
     v = -1;
     cnt = 0;
     if (m >= n_batches) return;
-    const long long a = batch_start(m);
-    const long long left = p.N - a;
-    cnt = left <= 0 ? 0 : (left < 32 ? (int)left : 32);
+    const int a = batch_start(m);
+    const int left = Ni - a;
+    cnt = left <= 0 ? 0 : (left < 32 ? left : 32);
     if (lane < cnt) {
       if (has_tok) {
         pos = __ldg(p.order + a + lane);
@@ -494,8 +540,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   load_batch(1, posB, vB, cntB);
 
   // ---- ring: occurrence n of this warp lives in stage n % D ----
-  long long issued = 0, consumed = 0;
-  int iw = 0, ik = 0;  // issue cursor: batch (0 = A, 1 = B) and entry
+  int issued = 0, consumed = 0;  // occurrences of this warp (< 2^31)
+  int is = 0;                    // stage of the next issue  (issued % D)
+  int cs = 0;                    // stage of the next consume (consumed % D)
+  int ps = 0;                    // stage of the previous consume
+  uint32_t cpar = 0;             // mbarrier parity of the next consume ((consumed / D) & 1)
+  int iw = 0, ik = 0;            // issue cursor: batch (0 = A, 1 = B) and entry
   auto try_issue = [&]() -> bool {
     for (;;) {
       const int cnt = iw ? cntB : cntA;
@@ -507,13 +557,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
     const int pos = __shfl_sync(0xffffffffu, iw ? posB : posA, ik);
     const int v = __shfl_sync(0xffffffffu, iw ? vB : vA, ik);
     if (lane == 0) {
-      const int s = (int)(issued % D);
-      unsigned char* st = ring + (size_t)s * L.stage_bytes;
-      mbar_expect_tx(bars + s, g_bytes + t_bytes);
-      bulk_g2s(st, gout + (size_t)pos * p.Do, g_bytes, bars + s);
-      if (has_tok) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + s);
+      unsigned char* st = ring + (size_t)is * L.stage_bytes;
+      mbar_expect_tx(bars + is, g_bytes + t_bytes);
+      bulk_g2s(st, gout + (size_t)pos * p.Do, g_bytes, bars + is);
+      if (has_tok) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + is);
     }
     ++issued;
+    if (++is == D) is = 0;
     ++ik;
     return true;
   };
@@ -537,6 +587,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   const bool tok_norm = C::tok_norm(p), out_norm = C::out_norm(p), byte_scale = C::byte_scale(p);
   float dlam_t = 0.f, dlam_b = 0.f;  // per-lane partials
   float* accp = p.byte_acc + (size_t)(gw % p.n_rep) * p.Vb * p.bd;
+  const float inv_Dt = 1.f / (float)(p.Dt > 0 ? p.Dt : 1), inv_Do = 1.f / (float)p.Do;
+  const bool id_lane = has_bytes && lane < p.bpt;
+  const IdSrc idsrc = make_id_src(p, lane);
 
   // ---- phase Z: rows nobody gathered get zeros (the dense-grad contract of the reference) ----
   if (has_tok) {
@@ -566,8 +619,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   float tscale = lam_t;   // lam_t * r_t of the current row
 
   // flush the current row segment: direct write if the whole row lies inside this chunk, else fp32 partial
-  auto flush = [&](long long chunk, bool trail) {
-    const T* trow = reinterpret_cast<const T*>(ring + (size_t)((consumed - 1) % D) * L.stage_bytes + L.g_bytes);
+  auto flush = [&](int chunk, bool trail) {
+    const T* trow = reinterpret_cast<const T*>(ring + (size_t)ps * L.stage_bytes + L.g_bytes);
     if (!seg_lead && !trail) {
       const float d = finish_tok_row<T, CPL, MODE>(p, cm, cur_v, Du, trow, lam_t);
       if (lane == 0) dlam_t += d;
@@ -575,7 +628,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       float* prow = p.partial + (size_t)(2 * chunk + (seg_lead ? 0 : 1)) * p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
-        if (cm[it].toff >= 0) {
+        if (MOT_TOK_OK(it)) {
           *reinterpret_cast<float4*>(prow + cm[it].toff) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
           *reinterpret_cast<float4*>(prow + cm[it].toff + 4) = make_float4(Du[it][4], Du[it][5], Du[it][6], Du[it][7]);
         }
@@ -587,14 +640,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
   };
 
-  for (long long m = 0; m < n_batches; ++m) {
-    const long long chunk = gw + (m / bpc) * W;
+  for (int m = 0; m < n_batches; ++m) {
+    const int chunk = gw + (m / bpc) * W;
     const bool chunk_first = (m % bpc) == 0, chunk_last = (m % bpc) == bpc - 1;
-    const long long a = batch_start(m);
+    const int a = batch_start(m);
     int v_before = -1;
     if (has_tok && chunk_first && a > 0 && cntA > 0) v_before = __ldg(p.stok + a - 1);
     const int pos_first = __shfl_sync(0xffffffffu, posA, 0);  // warp collective: outside lane-dependent branches
-    int id_next = (has_bytes && lane < p.bpt && cntA > 0) ? fetch_id(p, pos_first, lane) : 0;
+    int id_next = (id_lane && cntA > 0) ? load_raw_id(p, idsrc, pos_first, lane) : 0;
     for (int k = 0; k < cntA; ++k) {
       const int pos = __shfl_sync(0xffffffffu, posA, k);
       const int v = __shfl_sync(0xffffffffu, vA, k);
@@ -606,21 +659,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       }
       while (issued - consumed < D && try_issue()) {
       }
-      const int idreg = id_next;
+      const int idreg = clamp_id(p, id_next);
       const int pos_ahead = __shfl_sync(0xffffffffu, posA, (k + 1) & 31);
-      if (has_bytes && lane < p.bpt && k + 1 < cntA) id_next = fetch_id(p, pos_ahead, lane);
+      if (id_lane && k + 1 < cntA) id_next = load_raw_id(p, idsrc, pos_ahead, lane);
 
-      const int s = (int)(consumed % D);
-      mbar_wait(bars + s, (uint32_t)((consumed / D) & 1));
+      mbar_wait(bars + cs, cpar);
       ++consumed;
-      const T* grow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes);
-      const T* trow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes + L.g_bytes);
+      const T* grow = reinterpret_cast<const T*>(ring + (size_t)cs * L.stage_bytes);
+      const T* trow = reinterpret_cast<const T*>(ring + (size_t)cs * L.stage_bytes + L.g_bytes);
+      ps = cs;
+      if (++cs == D) {
+        cs = 0;
+        cpar ^= 1u;
+      }
 
       if (new_row && tok_norm) {
         float ss_t = 0.f;
 #pragma unroll
         for (int it = 0; it < CPL; ++it) {
-          if (cm[it].toff >= 0) {
+          if (MOT_TOK_OK(it)) {
             float tv[8];
             Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), tv);
 #pragma unroll
@@ -628,7 +685,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
           }
         }
         ss_t = warp_sum(ss_t);
-        tscale = lam_t * rsqrtf(ss_t / (float)p.Dt + p.eps);
+        tscale = lam_t * rsqrtf(ss_t * inv_Dt + p.eps);
       }
 
       int idv[CPL];  // byte id of this lane's slot per chunk (warp collective: outside lane-dependent branches)
@@ -639,7 +696,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       float ss = 0.f, gz = 0.f;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
-        if (has_tok && cm[it].toff >= 0) {
+        if (has_tok && MOT_TOK_OK(it)) {
           Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), z[it]);
           if (MODE == 0) {
 #pragma unroll
@@ -655,7 +712,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
               const int id = __shfl_sync(0xffffffffu, idreg, kk);
               if (cm[it].slot == -2) {
                 float b[8];
-                Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z[it][e] += bs * b[e];
@@ -663,9 +720,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
             }
           } else {
             const int id = idv[it];
-            if (cm[it].slot >= 0) {
+            if (MOT_BYTE_OK(it)) {
               float b[8];
-              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               if (byte_scale) {
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
@@ -678,7 +735,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
           }
         }
         if (out_norm) {
-          if (it * 32 + lane < p.n_chunks) {
+          if (MOT_CHUNK_OK(it)) {
             float g[8];
             Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), g);
 #pragma unroll
@@ -692,12 +749,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       float r_o = 1.f, coef = 0.f;
       if (out_norm) {
         warp_sum2(ss, gz);
-        r_o = rsqrtf(ss / (float)p.Do + p.eps);
-        coef = r_o * r_o * r_o * gz / (float)p.Do;
+        r_o = rsqrtf(ss * inv_Do + p.eps);
+        coef = r_o * r_o * r_o * gz * inv_Do;
       }
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
-        const bool valid = it * 32 + lane < p.n_chunks;  // lane-dependent: no warp collectives under it
+        const bool valid = MOT_CHUNK_OK(it);  // lane-dependent: no warp collectives under it
         float dz[8];
         if (valid) {
           Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), dz);
@@ -705,7 +762,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
             for (int e = 0; e < 8; ++e) dz[e] = r_o * dz[e] - coef * z[it][e];
           }
-          if (cm[it].toff >= 0) {
+          if (MOT_TOK_OK(it)) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) Du[it][e] += dz[e];
           }
@@ -720,7 +777,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
               if (valid && cm[it].slot == -2) {
                 if (has_lam) {
                   float b[8];
-                  Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                  Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
                   const float r = rs[id] * inv_pool;
 #pragma unroll
                   for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
@@ -731,11 +788,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
                 gmem_add8(accp + (size_t)id * p.bd + cm[it].boff, dzs);
               }
             }
-          } else if (valid && cm[it].slot >= 0) {
+          } else if (valid && MOT_BYTE_OK(it)) {
             const int id = idv[it];
             if (has_lam) {  // d lam_byte += <dz, bhat>
               float b[8];
-              Vec8<T>::unpack(tab_load<T>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               const float r = rs[id];
 #pragma unroll
               for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
@@ -753,8 +810,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
     // end of batch: at the end of a chunk the open row segment is flushed
     if (chunk_last || m + 1 == n_batches || cntB == 0) {
       if (has_tok && cur_v >= 0) {
-        const long long b_end = chunk * (long long)p.R + p.R;
-        const bool trail = b_end < p.N && __ldg(p.stok + b_end) == cur_v;
+        const int b_end = chunk * p.R + p.R;
+        const bool trail = b_end < Ni && __ldg(p.stok + b_end) == cur_v;
         flush(chunk, trail);
         cur_v = -1;
         seg_lead = false;
@@ -806,14 +863,15 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
       const long long c1 = (o1 - 1) / p.R;                     // last chunk of the row
       const T* trow = E_tok + (size_t)v * p.Dt;
       float dot = 0.f, ss = 0.f;
-      for (int pass = 0; pass < 2; ++pass) {
+      // pass 0 (only when the token-norm backward or d lam_tok need <Du, t> and |t|^2), pass 1 writes the row
+      for (int pass = (tok_norm || has_lam) ? 0 : 1; pass < 2; ++pass) {
         const float r_t = tok_norm ? rsqrtf(ss / (float)p.Dt + p.eps) : 1.f;
         const float a_ = lam_t * r_t;
         const float b_ = tok_norm ? lam_t * r_t * r_t * r_t * dot / (float)p.Dt : 0.f;
         float dacc = 0.f, sacc = 0.f;
         for (int c = lane; c < p.Dt / kChunk; c += 32) {
-          float tv[8], du[8];
-          Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
+          float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, du[8];
+          if (tok_norm || has_lam) Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
           {
             const float* pr = p.partial + (size_t)(2 * c0 + 1) * p.Dt + c * kChunk;  // trailing partial of c0
             const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
@@ -847,42 +905,52 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
     }
   }
   if (has_bytes) {
+    // one warp per byte row, one lane per 8-element chunk; the kByteRep replica loads are independent (unrolled)
     const bool bn = (p.flags & MOT_F_BYTE_NORM) != 0;
     const T* E_byte = reinterpret_cast<const T*>(p.E_byte);
     T* G = reinterpret_cast<T*>(p.gE_byte);
     const size_t rep_stride = (size_t)p.Vb * p.bd;
-    for (int r = gw; r < p.Vb; r += W) {
-      float dot = 0.f, ss = 0.f;
-      for (int pass = 0; pass < 2; ++pass) {
-        const float rsr = bn ? rsqrtf(ss / (float)p.bd + p.eps) : 1.f;
-        const float b_ = bn ? rsr * rsr * rsr * dot / (float)p.bd : 0.f;
-        float dacc = 0.f, sacc = 0.f;
-        if (pass == 0 && !bn) continue;
-        for (int c = lane; c < p.bd / kChunk; c += 32) {
-          float ev[8], a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
-          for (int rep = 0; rep < p.n_rep; ++rep) {
-            const float* src = p.byte_acc + rep * rep_stride + (size_t)r * p.bd + c * kChunk;
-            const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
-            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w; a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
-          }
-          if (pass == 0) {
+    const int nc = p.bd / kChunk;
+    // byte rows are the tasks after the chunk boundaries, so a grid of (boundaries + Vb) warps gives one task per warp
+    const int nb_ = has_tok ? (int)((p.N + p.R - 1) / p.R) - 1 : 0;
+    for (int t_ = gw; t_ < nb_ + p.Vb; t_ += W) {
+      const int r = t_ - nb_;
+      if (r < 0) continue;
+      for (int c0 = 0; c0 < nc; c0 += 32) {  // bd <= 256 for every reference config: one trip
+        const int c = c0 + lane;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (c < nc) {
+          const float* src = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+          float4 x[kByteRep], y[kByteRep];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              dacc += a[e] * ev[e];
-              sacc += ev[e] * ev[e];
-            }
-          } else {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = rsr * a[e] - b_ * ev[e];
-            Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, o);
+          for (int rep = 0; rep < kByteRep; ++rep) {
+            x[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride);
+            y[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride + 4);
           }
+#pragma unroll
+          for (int rep = 0; rep < kByteRep; ++rep) {
+            a[0] += x[rep].x; a[1] += x[rep].y; a[2] += x[rep].z; a[3] += x[rep].w;
+            a[4] += y[rep].x; a[5] += y[rep].y; a[6] += y[rep].z; a[7] += y[rep].w;
+          }
+          if (bn) Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
         }
-        if (pass == 0) {
-          warp_sum2(dacc, sacc);
-          dot = dacc;
-          ss = sacc;
+        float rsr = 1.f, b_ = 0.f;
+        if (bn) {  // rows wider than 256 elements would need a cross-trip reduction; refused on the host
+          float dot = 0.f, ss = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            dot += a[e] * ev[e];
+            ss += ev[e] * ev[e];
+          }
+          warp_sum2(dot, ss);
+          rsr = rsqrtf(ss / (float)p.bd + p.eps);
+          b_ = rsr * rsr * rsr * dot / (float)p.bd;
+        }
+        if (c < nc) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = rsr * a[e] - b_ * ev[e];
+          Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, o);
         }
       }
     }
@@ -898,7 +966,8 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
 // ======================================================================================
 // Pick the ring depth and whether the byte table fits next to it; returns dynamic smem bytes or 0.
 inline size_t plan_smem(EmbedParams& p, size_t esz, int warps, bool backward, int optin) {
-  const int want = backward ? 4 : 4;
+  static const char* env_st = getenv("MOT_STAGES");  // debug knob
+  const int want = env_st ? atoi(env_st) : 4;
   p.tab_smem = 1;
   for (int tab = 1; tab >= 0; --tab) {
     p.tab_smem = tab;
@@ -918,6 +987,7 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   EmbedParams p = p_in;
   const size_t smem = plan_smem(p, sizeof(T), kFwdThreads / 32, false, optin);
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
+  if (MODE == 1 && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
   auto kern = mot_fwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   const long long warps_needed = p.N;
@@ -938,6 +1008,7 @@ static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   EmbedParams p = p_in;
   const size_t smem = plan_smem(p, sizeof(T), kBwdThreads / 32, true, optin);
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
+  if (MODE == 1 && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
   auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
