@@ -58,17 +58,27 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// 8 consecutive elements <-> 8 floats.  Pointers must be 16-byte aligned.  `Raw` is the
-// register image of the 8 elements as loaded (kept packed while a load is in flight).
-template <typename T>
-struct Vec8;
+// CW consecutive elements <-> CW floats (CW = 8: 16 B of bf16 / 32 B of fp32; CW = 4: 8 B / 16 B).  Pointers must be
+// aligned to the access size.  `Raw` is the register image of the elements as loaded (kept packed while a load is
+// in flight).
+__device__ __forceinline__ uint2 ldg_nc_8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_8(void* p, const uint2& v) {
+  asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_8(const void* p) { return *reinterpret_cast<const uint2*>(p); }
+
+template <typename T, int CW>
+struct Vec;
 
 template <>
-struct Vec8<__nv_bfloat16> {
+struct Vec<__nv_bfloat16, 8> {
   using Raw = uint4;
   __device__ __forceinline__ static Raw ldg_raw(const __nv_bfloat16* p) { return ldg_nc_16(p); }
   __device__ __forceinline__ static Raw lds_raw(const __nv_bfloat16* p) { return lds_16(p); }
-  __device__ __forceinline__ static Raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[8]) {
     bf16x2_to_f32(r.x, v[0], v[1]);
     bf16x2_to_f32(r.y, v[2], v[3]);
@@ -86,13 +96,29 @@ struct Vec8<__nv_bfloat16> {
 };
 
 template <>
-struct Vec8<float> {
+struct Vec<__nv_bfloat16, 4> {
+  using Raw = uint2;
+  __device__ __forceinline__ static Raw ldg_raw(const __nv_bfloat16* p) { return ldg_nc_8(p); }
+  __device__ __forceinline__ static Raw lds_raw(const __nv_bfloat16* p) { return lds_8(p); }
+  __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[4]) {
+    bf16x2_to_f32(r.x, v[0], v[1]);
+    bf16x2_to_f32(r.y, v[2], v[3]);
+  }
+  __device__ __forceinline__ static void stg(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 r;
+    r.x = f32x2_to_bf16x2(v[0], v[1]);
+    r.y = f32x2_to_bf16x2(v[2], v[3]);
+    stg_8(p, r);
+  }
+};
+
+template <>
+struct Vec<float, 8> {
   struct Raw {
     uint4 a, b;
   };
   __device__ __forceinline__ static Raw ldg_raw(const float* p) { return Raw{ldg_nc_16(p), ldg_nc_16(p + 4)}; }
   __device__ __forceinline__ static Raw lds_raw(const float* p) { return Raw{lds_16(p), lds_16(p + 4)}; }
-  __device__ __forceinline__ static Raw zero_raw() { return Raw{make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}; }
   __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[8]) {
     v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
     v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
@@ -105,6 +131,24 @@ struct Vec8<float> {
     stg_16(p + 4, b);
   }
 };
+
+template <>
+struct Vec<float, 4> {
+  using Raw = uint4;
+  __device__ __forceinline__ static Raw ldg_raw(const float* p) { return ldg_nc_16(p); }
+  __device__ __forceinline__ static Raw lds_raw(const float* p) { return lds_16(p); }
+  __device__ __forceinline__ static void unpack(const Raw& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+  __device__ __forceinline__ static void stg(float* p, const float (&v)[4]) {
+    uint4 a;
+    a.x = __float_as_uint(v[0]); a.y = __float_as_uint(v[1]); a.z = __float_as_uint(v[2]); a.w = __float_as_uint(v[3]);
+    stg_16(p, a);
+  }
+};
+
+template <typename T>
+using Vec8 = Vec<T, 8>;
 
 // ---- mbarrier + 1-D bulk (TMA) copy global -> shared, used to stage the byte table ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -121,9 +121,13 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.ttb_dtype = d->ttb_dtype;
   p.n_chunks = d->out_dim / kChunk;
   p.eps = d->eps;
-  // stream chunk size: 32 entries, grown so that there are at most ~4096 chunks (bounds the partial-row scratch)
-  long long R = 32;
-  while (d->n_tokens / R > 4096) R <<= 1;
+  // stream chunk size: one chunk per backward warp of a full B200 (148 SMs x kBwdThreads/32 warps), so that every
+  // warp walks the same number of stream entries; chunks longer than one 32-entry batch are whole batches.
+  // (A constant, not the current device's SM count: the workspace layout must not depend on the device.)
+  const long long warps = 148LL * (kBwdThreads / 32);
+  long long R = (d->n_tokens + warps - 1) / warps;
+  if (R < 1) R = 1;
+  if (R > 32) R = (R + 31) / 32 * 32;
   p.R = (int)R;
   p.n_rep = kByteRep;
   p.stages = 4;

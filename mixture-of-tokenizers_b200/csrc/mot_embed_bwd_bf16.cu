@@ -4,18 +4,17 @@ namespace mot {
 int dispatch_bwd_wide_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
-  const int cpl = (p.n_chunks + 31) / 32;
-  if (pick_mode(p) == 1) {  // MoT-sum fast path (runs/71)
-    if (cpl == 3) return launch_bwd<T, 3, 1>(p, s);
+  const int cpl = (p.Do + 32 * kBwdCW - 1) / (32 * kBwdCW);  // 4-element chunks per lane
+  if (pick_mode(p, kBwdCW) == 1) {  // MoT-sum fast path (runs/71): 512 = 8 x 64, 768 = 16 x 48, 1024 = 16 x 64 / 8 x 128 / 32 x 32
     if (cpl == 4) return launch_bwd<T, 4, 1>(p, s);
+    if (cpl == 6) return launch_bwd<T, 6, 1>(p, s);
+    if (cpl == 8) return launch_bwd<T, 8, 1>(p, s);
   }
-  switch (cpl) {
-    case 1: return launch_bwd<T, 1, 0>(p, s);
-    case 2: return launch_bwd<T, 2, 0>(p, s);
-    case 3: return launch_bwd<T, 3, 0>(p, s);
-    case 4: return launch_bwd<T, 4, 0>(p, s);
-    default: return dispatch_bwd_wide_bf16(p, s);
-  }
+  if (cpl <= 2) return launch_bwd<T, 2, 0>(p, s);
+  if (cpl <= 4) return launch_bwd<T, 4, 0>(p, s);
+  if (cpl <= 6) return launch_bwd<T, 6, 0>(p, s);
+  if (cpl <= 8) return launch_bwd<T, 8, 0>(p, s);
+  return dispatch_bwd_wide_bf16(p, s);
 }
 int launch_finalize_bf16(const EmbedParams& p, int blocks, cudaStream_t s) {
   mot_bwd_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p);

@@ -4,14 +4,12 @@ namespace mot {
 int dispatch_bwd_wide_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s) {
   using T = float;
-  const int cpl = (p.n_chunks + 31) / 32;
-  switch (cpl) {
-    case 1: return launch_bwd<T, 1, 0>(p, s);
-    case 2: return launch_bwd<T, 2, 0>(p, s);
-    case 3: return launch_bwd<T, 3, 0>(p, s);
-    case 4: return launch_bwd<T, 4, 0>(p, s);
-    default: return dispatch_bwd_wide_f32(p, s);
-  }
+  const int cpl = (p.Do + 32 * kBwdCW - 1) / (32 * kBwdCW);
+  if (cpl <= 2) return launch_bwd<T, 2, 0>(p, s);
+  if (cpl <= 4) return launch_bwd<T, 4, 0>(p, s);
+  if (cpl <= 6) return launch_bwd<T, 6, 0>(p, s);
+  if (cpl <= 8) return launch_bwd<T, 8, 0>(p, s);
+  return dispatch_bwd_wide_f32(p, s);
 }
 int launch_finalize_f32(const EmbedParams& p, int blocks, cudaStream_t s) {
   mot_bwd_finalize_kernel<float><<<blocks, 256, 0, s>>>(p);

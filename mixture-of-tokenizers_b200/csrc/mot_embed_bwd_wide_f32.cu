@@ -3,10 +3,9 @@
 namespace mot {
 int dispatch_bwd_wide_f32(const EmbedParams& p, cudaStream_t s) {
   using T = float;
-  switch ((p.n_chunks + 31) / 32) {
-    case 5: case 6: return launch_bwd<T, 6, 0>(p, s);
-    case 7: case 8: return launch_bwd<T, 8, 0>(p, s);
-  }
+  const int cpl = (p.Do + 32 * kBwdCW - 1) / (32 * kBwdCW);
+  if (cpl <= 12) return launch_bwd<T, 12, 0>(p, s);
+  if (cpl <= 16) return launch_bwd<T, 16, 0>(p, s);
   return MOT_ERR_UNSUPPORTED;
 }
 }  // namespace mot

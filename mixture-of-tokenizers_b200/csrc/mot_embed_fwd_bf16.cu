@@ -4,7 +4,7 @@ namespace mot {
 int dispatch_fwd_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
   const int cpl = (p.n_chunks + 31) / 32;
-  if (pick_mode(p) == 1) {  // MoT-sum fast path (runs/71), the shapes the reference ships
+  if (pick_mode(p, 8) == 1) {  // MoT-sum fast path (runs/71), the shapes the reference ships
     if (cpl == 3) return launch_fwd<T, 3, 1>(p, s);
     if (cpl == 4) return launch_fwd<T, 4, 1>(p, s);
   }

@@ -66,10 +66,11 @@ struct ChunkMap {
   int boff;  // element offset inside the byte row
 };
 
+template <int CW>
 __device__ __forceinline__ ChunkMap chunk_map(const EmbedParams& p, int c) {
   ChunkMap m{-1, -1, 0};
-  if (c >= p.n_chunks) return m;
-  const int e = c * kChunk;
+  if (c * CW >= p.Do) return m;
+  const int e = c * CW;
   switch (p.combine) {
     case MOT_ADD:
       m.toff = e;
@@ -170,19 +171,19 @@ struct Cfg {
   __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || p.combine != MOT_TOK_ONLY; }
   __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MODE == 0 && p.combine == MOT_MEAN; }
 };
-inline int pick_mode(const EmbedParams& p) {
+inline int pick_mode(const EmbedParams& p, int cw) {
   const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
-  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.n_chunks % 32 == 0 && p.tab_smem) ? 1 : 0;
+  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.Do % (32 * cw) == 0 && p.tab_smem) ? 1 : 0;
 }
 
 #define MOT_TOK_OK(it) (MODE == 1 || cm[it].toff >= 0)
 #define MOT_BYTE_OK(it) (MODE == 1 || cm[it].slot >= 0)
-#define MOT_CHUNK_OK(it) (MODE == 1 || (it) * 32 + lane < p.n_chunks)
+#define MOT_CHUNK_OK(it) (MODE == 1 || ((it) * 32 + lane) * CW < p.Do)
 
-template <typename T, int MODE = 0>
-__device__ __forceinline__ typename Vec8<T>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
-  if (MODE == 1) return Vec8<T>::lds_raw(tab + off);  // the fast path is only dispatched when the table fits
-  return p.tab_smem ? Vec8<T>::lds_raw(tab + off) : Vec8<T>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
+template <typename T, int MODE = 0, int CW = 8>
+__device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
+  if (MODE == 1) return Vec<T, CW>::lds_raw(tab + off);  // the fast path is only dispatched when the table fits
+  return p.tab_smem ? Vec<T, CW>::lds_raw(tab + off) : Vec<T, CW>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
 // Stage E_byte into shared memory (bulk async copies of <= 32 KB) and compute the per-row rms scale
@@ -244,15 +245,17 @@ __host__ __device__ inline SmemLayout smem_layout(const EmbedParams& p, size_t e
   return L;
 }
 
-// fp32 accumulate of 8 consecutive values into the L2-resident scratch: two RED.E.ADD.F32x4 (no return value,
-// no dependency chain).  Shared-memory fp32 atomics would be CAS spin loops (measured 1.4x slower end to end).
-__device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
+// fp32 accumulate of 4 consecutive values into the L2-resident scratch: one RED.E.ADD.F32x4 (no return value, no
+// dependency chain).  A warp-wide instruction covers 512 contiguous bytes per byte row piece: the L2 atomic units work
+// per 32-byte sector, so two lanes fill one sector per request (tools/ubench/red_bench.cu: 28.8 us for the 37.7 M adds
+// of the 48K-token workload, against 49.0 us when a lane owns 8 consecutive floats and issues two half-sector REDs;
+// shared-memory fp32 atomics are CAS spin loops, 47.3 us).
+__device__ __forceinline__ void gmem_add4(float* a, const float (&v)[4]) {
 #ifdef MOT_EXPERIMENT_NO_RED
   if (v[0] == 12345.678f) a[0] = v[1];
   return;
 #endif
   atomicAdd(reinterpret_cast<float4*>(a), make_float4(v[0], v[1], v[2], v[3]));
-  atomicAdd(reinterpret_cast<float4*>(a) + 1, make_float4(v[4], v[5], v[6], v[7]));
 }
 
 // ======================================================================================
@@ -261,7 +264,7 @@ __device__ __forceinline__ void gmem_add8(float* a, const float (&v)[8]) {
 template <typename T, int CPL, int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedParams p) {
   using C = Cfg<MODE>;
-  using Raw = typename Vec8<T>::Raw;
+  constexpr int CW = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t tab_bar;
   const int lane = lane_id();
@@ -281,7 +284,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
   fence_mbar_init();
   __syncthreads();
 
-  const int gw = blockIdx.x * nw + warp;   // n_tokens < 2^31 (validated on the host): 32-bit position math
+  const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs: every SM gets the same share +-1
+                                                 // (n_tokens < 2^31, validated on the host: 32-bit position math)
   const int stride = gridDim.x * nw;
   const int Ni = (int)p.N;
   const int n_i = gw < Ni ? (Ni - gw + stride - 1) / stride : 0;  // positions of this warp
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
 
   ChunkMap cm[CPL];
 #pragma unroll
-  for (int it = 0; it < CPL; ++it) cm[it] = chunk_map(p, it * 32 + lane);
+  for (int it = 0; it < CPL; ++it) cm[it] = chunk_map<CW>(p, it * 32 + lane);
 
   float lam_t = 1.f, lam_b = 1.f;
   if (C::has_lam(p)) {
@@ -429,12 +433,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
 // ======================================================================================
 // Backward
 // ======================================================================================
+// The backward kernel uses 4-element chunks (CW = 4): chunk c = it*32 + lane, so every warp-wide access is a contiguous
+// 256 B (bf16) / 512 B (fp32) segment and the byte-gradient REDs fill whole 32-byte sectors (see gmem_add4).
+constexpr int kBwdCW = 4;
+
 // Finish one token row: Du = sum over its occurrences of d z[token part]; tv = the raw token row (shared or
 // global memory); writes d E_tok[v] and returns <Du, that> (the row's contribution to d lam_tok).
 template <typename T, int CPL, int MODE>
-__device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const ChunkMap (&cm)[CPL], int v, float (&Du)[CPL][8],
+__device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const ChunkMap (&cm)[CPL], int v, float (&Du)[CPL][kBwdCW],
                                                 const T* trow_smem, float lam_t) {
   using C = Cfg<MODE>;
+  constexpr int CW = kBwdCW;
+  using V = Vec<T, CW>;
   const bool tok_norm = C::tok_norm(p);
   const bool need_t = tok_norm || C::has_lam(p);
   float dot = 0.f, ss = 0.f;  // <Du, tv>, |tv|^2
@@ -442,10 +452,10 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
       if (MOT_TOK_OK(it)) {
-        float tv[8];
-        Vec8<T>::unpack(Vec8<T>::lds_raw(trow_smem + cm[it].toff), tv);
+        float tv[CW];
+        V::unpack(V::lds_raw(trow_smem + cm[it].toff), tv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < CW; ++e) {
           dot += Du[it][e] * tv[e];
           ss += tv[e] * tv[e];
         }
@@ -461,28 +471,37 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
 #pragma unroll
   for (int it = 0; it < CPL; ++it) {
     if (MOT_TOK_OK(it)) {
-      float o[8];
+      float o[CW];
       if (tok_norm) {
-        float tv[8];
-        Vec8<T>::unpack(Vec8<T>::lds_raw(trow_smem + cm[it].toff), tv);
+        float tv[CW];
+        V::unpack(V::lds_raw(trow_smem + cm[it].toff), tv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = a * Du[it][e] - b * tv[e];
+        for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e] - b * tv[e];
       } else if (MODE == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = a * Du[it][e];
+        for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e];
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = Du[it][e];
+        for (int e = 0; e < CW; ++e) o[e] = Du[it][e];
       }
-      Vec8<T>::stg(grow + cm[it].toff, o);
+      V::stg(grow + cm[it].toff, o);
     }
   }
   return r_t * dot;
 }
 
+// One batch of the token-sorted stream: up to 32 consecutive entries, one per lane.
+struct Batch {
+  int pos, v;      // per lane: position and token id of entry `lane`
+  int cnt;         // valid entries (0: the stream is exhausted)
+  int chunk, sub;  // stream chunk and batch index inside the chunk
+};
+
 template <typename T, int CPL, int MODE>
 __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedParams p) {
   using C = Cfg<MODE>;
+  constexpr int CW = kBwdCW;
+  using V = Vec<T, CW>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t tab_bar;
   const int lane = lane_id();
@@ -502,42 +521,51 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   fence_mbar_init();
   __syncthreads();
 
-  const int gw = blockIdx.x * nw + warp;
+  const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs
   const int W = gridDim.x * nw;
   const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
   const T* gout = reinterpret_cast<const T*>(p.gout);
   const uint32_t g_bytes = (uint32_t)p.Do * sizeof(T);
   const uint32_t t_bytes = has_tok ? (uint32_t)p.Dt * sizeof(T) : 0u;
 
-  // ---- the warp's share of the token-sorted stream: chunks gw, gw+W, ... of R entries, walked in
-  //      batches of 32 entries (one per lane) ----
+  // ---- the warp's share of the token-sorted stream: chunks gw, gw+W, ... of R entries (gw is interleaved over the
+  //      CTAs, so every SM gets the same number of chunks +-1), walked in batches of 32 entries (one per lane) ----
   const int Ni = (int)p.N;  // n_tokens < 2^31 (validated on the host): 32-bit stream math
   const int n_stream_chunks = (Ni + p.R - 1) / p.R;
-  const int bpc = p.R / 32;  // batches per chunk
-  const int my_chunks = gw < n_stream_chunks ? (n_stream_chunks - gw + W - 1) / W : 0;
-  const int n_batches = my_chunks * bpc;
-  auto batch_start = [&](int m) -> int { return (gw + (m / bpc) * W) * p.R + (m % bpc) * 32; };
-  auto load_batch = [&](int m, int& pos, int& v, int& cnt) {
-    pos = 0;
-    v = -1;
-    cnt = 0;
-    if (m >= n_batches) return;
-    const int a = batch_start(m);
-    const int left = Ni - a;
-    cnt = left <= 0 ? 0 : (left < 32 ? left : 32);
-    if (lane < cnt) {
+  const int bpc = (p.R + 31) / 32;  // batches per chunk
+  int nx_chunk = gw, nx_sub = 0;    // the next batch to load
+  auto load_next = [&](Batch& b) {
+    b.pos = 0;
+    b.v = -1;
+    b.cnt = 0;
+    b.chunk = -1;
+    b.sub = 0;
+    if (nx_chunk >= n_stream_chunks) return;
+    const int a = nx_chunk * p.R + nx_sub * 32;  // < Ni by construction
+    const int c_end = min(nx_chunk * p.R + p.R, Ni);
+    const int left = c_end - a;
+    b.cnt = left < 32 ? left : 32;
+    b.chunk = nx_chunk;
+    b.sub = nx_sub;
+    if (lane < b.cnt) {
       if (has_tok) {
-        pos = __ldg(p.order + a + lane);
-        v = __ldg(p.stok + a + lane);
+        b.pos = __ldg(p.order + a + lane);
+        b.v = __ldg(p.stok + a + lane);
       } else {
-        pos = (int)(a + lane);  // bytes-only: no token table, the stream is the position order
-        v = 0;
+        b.pos = a + lane;  // bytes-only: no token table, the stream is the position order
+        b.v = 0;
       }
     }
+    if (a + 32 >= c_end) {
+      nx_chunk += W;
+      nx_sub = 0;
+    } else {
+      ++nx_sub;
+    }
   };
-  int posA, vA, cntA, posB, vB, cntB;
-  load_batch(0, posA, vA, cntA);
-  load_batch(1, posB, vB, cntB);
+  Batch A, B;
+  load_next(A);
+  load_next(B);
 
   // ---- ring: occurrence n of this warp lives in stage n % D ----
   int issued = 0, consumed = 0;  // occurrences of this warp (< 2^31)
@@ -548,14 +576,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   int iw = 0, ik = 0;            // issue cursor: batch (0 = A, 1 = B) and entry
   auto try_issue = [&]() -> bool {
     for (;;) {
-      const int cnt = iw ? cntB : cntA;
+      const int cnt = iw ? B.cnt : A.cnt;
       if (ik < cnt) break;
       if (iw == 1) return false;  // ran past the prefetched batch: wait for the consumer to advance
       iw = 1;
       ik = 0;
     }
-    const int pos = __shfl_sync(0xffffffffu, iw ? posB : posA, ik);
-    const int v = __shfl_sync(0xffffffffu, iw ? vB : vA, ik);
+    const int pos = __shfl_sync(0xffffffffu, iw ? B.pos : A.pos, ik);
+    const int v = __shfl_sync(0xffffffffu, iw ? B.v : A.v, ik);
     if (lane == 0) {
       unsigned char* st = ring + (size_t)is * L.stage_bytes;
       mbar_expect_tx(bars + is, g_bytes + t_bytes);
@@ -574,7 +602,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 
   ChunkMap cm[CPL];
 #pragma unroll
-  for (int it = 0; it < CPL; ++it) cm[it] = chunk_map(p, it * 32 + lane);
+  for (int it = 0; it < CPL; ++it) cm[it] = chunk_map<CW>(p, it * 32 + lane);
 
   const bool has_lam = C::has_lam(p);
   float lam_t = 1.f, lam_b = 1.f;
@@ -594,7 +622,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   // ---- phase Z: rows nobody gathered get zeros (the dense-grad contract of the reference) ----
   if (has_tok) {
     T* G = reinterpret_cast<T*>(p.gE_tok);
-    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float zero[CW] = {0.f, 0.f, 0.f, 0.f};
     for (int vb = gw * 32; vb < p.V; vb += W * 32) {
       const int v = vb + lane;
       const bool empty = v < p.V && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
@@ -603,17 +631,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         const int j = __ffs(m) - 1;
         m &= m - 1;
         T* row = G + (size_t)(vb + j) * p.Dt;
-        for (int c = lane; c < p.Dt / kChunk; c += 32) Vec8<T>::stg(row + c * kChunk, zero);
+        for (int c = lane; c < p.Dt / CW; c += 32) V::stg(row + c * CW, zero);
       }
     }
   }
 
   // ---- phase S: the stream ----
-  float Du[CPL][8];
+  float Du[CPL][CW];
 #pragma unroll
   for (int it = 0; it < CPL; ++it)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
+    for (int e = 0; e < CW; ++e) Du[it][e] = 0.f;
   int cur_v = -1;
   bool seg_lead = false;  // current row segment started at the chunk start and continues a row of the previous chunk
   float tscale = lam_t;   // lam_t * r_t of the current row
@@ -628,29 +656,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       float* prow = p.partial + (size_t)(2 * chunk + (seg_lead ? 0 : 1)) * p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
-        if (MOT_TOK_OK(it)) {
+        if (MOT_TOK_OK(it))
           *reinterpret_cast<float4*>(prow + cm[it].toff) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
-          *reinterpret_cast<float4*>(prow + cm[it].toff + 4) = make_float4(Du[it][4], Du[it][5], Du[it][6], Du[it][7]);
-        }
       }
     }
 #pragma unroll
     for (int it = 0; it < CPL; ++it)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) Du[it][e] = 0.f;
+      for (int e = 0; e < CW; ++e) Du[it][e] = 0.f;
   };
 
-  for (int m = 0; m < n_batches; ++m) {
-    const int chunk = gw + (m / bpc) * W;
-    const bool chunk_first = (m % bpc) == 0, chunk_last = (m % bpc) == bpc - 1;
-    const int a = batch_start(m);
+  while (A.cnt > 0) {
+    const int chunk = A.chunk;
+    const int a = chunk * p.R + A.sub * 32;
+    const bool chunk_first = A.sub == 0, chunk_last = a + 32 >= min(chunk * p.R + p.R, Ni);
     int v_before = -1;
-    if (has_tok && chunk_first && a > 0 && cntA > 0) v_before = __ldg(p.stok + a - 1);
-    const int pos_first = __shfl_sync(0xffffffffu, posA, 0);  // warp collective: outside lane-dependent branches
-    int id_next = (id_lane && cntA > 0) ? load_raw_id(p, idsrc, pos_first, lane) : 0;
-    for (int k = 0; k < cntA; ++k) {
-      const int pos = __shfl_sync(0xffffffffu, posA, k);
-      const int v = __shfl_sync(0xffffffffu, vA, k);
+    if (has_tok && chunk_first && a > 0) v_before = __ldg(p.stok + a - 1);
+    const int pos_first = __shfl_sync(0xffffffffu, A.pos, 0);  // warp collective: outside lane-dependent branches
+    int id_next = id_lane ? load_raw_id(p, idsrc, pos_first, lane) : 0;
+    for (int k = 0; k < A.cnt; ++k) {
+      const int v = __shfl_sync(0xffffffffu, A.v, k);
       const bool new_row = has_tok && v != cur_v;
       if (new_row) {  // flush BEFORE refilling the ring: the old row's token row sits in stage (consumed-1) % D
         if (cur_v >= 0) flush(chunk, false);
@@ -660,8 +685,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       while (issued - consumed < D && try_issue()) {
       }
       const int idreg = clamp_id(p, id_next);
-      const int pos_ahead = __shfl_sync(0xffffffffu, posA, (k + 1) & 31);
-      if (id_lane && k + 1 < cntA) id_next = load_raw_id(p, idsrc, pos_ahead, lane);
+      const int pos_ahead = __shfl_sync(0xffffffffu, A.pos, (k + 1) & 31);
+      if (id_lane && k + 1 < A.cnt) id_next = load_raw_id(p, idsrc, pos_ahead, lane);
 
       mbar_wait(bars + cs, cpar);
       ++consumed;
@@ -678,10 +703,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
         for (int it = 0; it < CPL; ++it) {
           if (MOT_TOK_OK(it)) {
-            float tv[8];
-            Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), tv);
+            float tv[CW];
+            V::unpack(V::lds_raw(trow + cm[it].toff), tv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss_t += tv[e] * tv[e];
+            for (int e = 0; e < CW; ++e) ss_t += tv[e] * tv[e];
           }
         }
         ss_t = warp_sum(ss_t);
@@ -692,54 +717,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) idv[it] = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
       // z = tscale * t + lam_b * rs * b
-      float z[CPL][8];
+      float z[CPL][CW];
       float ss = 0.f, gz = 0.f;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (has_tok && MOT_TOK_OK(it)) {
-          Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), z[it]);
+          V::unpack(V::lds_raw(trow + cm[it].toff), z[it]);
           if (MODE == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) z[it][e] *= tscale;
+            for (int e = 0; e < CW; ++e) z[it][e] *= tscale;
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) z[it][e] = 0.f;
+          for (int e = 0; e < CW; ++e) z[it][e] = 0.f;
         }
         if (has_bytes) {
           if (C::mean(p)) {
             for (int kk = 0; kk < p.bpt; ++kk) {
               const int id = __shfl_sync(0xffffffffu, idreg, kk);
               if (cm[it].slot == -2) {
-                float b[8];
-                Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                float b[CW];
+                V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) z[it][e] += bs * b[e];
+                for (int e = 0; e < CW; ++e) z[it][e] += bs * b[e];
               }
             }
           } else {
             const int id = idv[it];
             if (MOT_BYTE_OK(it)) {
-              float b[8];
-              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              float b[CW];
+              V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               if (byte_scale) {
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) z[it][e] += bs * b[e];
+                for (int e = 0; e < CW; ++e) z[it][e] += bs * b[e];
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) z[it][e] += b[e];
+                for (int e = 0; e < CW; ++e) z[it][e] += b[e];
               }
             }
           }
         }
         if (out_norm) {
           if (MOT_CHUNK_OK(it)) {
-            float g[8];
-            Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), g);
+            float g[CW];
+            V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), g);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < CW; ++e) {
               ss += z[it][e] * z[it][e];
               gz += g[e] * z[it][e];
             }
@@ -755,20 +780,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         const bool valid = MOT_CHUNK_OK(it);  // lane-dependent: no warp collectives under it
-        float dz[8];
+        float dz[CW];
         if (valid) {
-          Vec8<T>::unpack(Vec8<T>::lds_raw(grow + (size_t)(it * 32 + lane) * kChunk), dz);
+          V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), dz);
           if (out_norm) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) dz[e] = r_o * dz[e] - coef * z[it][e];
+            for (int e = 0; e < CW; ++e) dz[e] = r_o * dz[e] - coef * z[it][e];
           }
           if (MOT_TOK_OK(it)) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) Du[it][e] += dz[e];
+            for (int e = 0; e < CW; ++e) Du[it][e] += dz[e];
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dz[e] = 0.f;
+          for (int e = 0; e < CW; ++e) dz[e] = 0.f;
         }
         if (has_bytes) {
           if (C::mean(p)) {
@@ -776,51 +801,49 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
               const int id = __shfl_sync(0xffffffffu, idreg, kk);
               if (valid && cm[it].slot == -2) {
                 if (has_lam) {
-                  float b[8];
-                  Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                  float b[CW];
+                  V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
                   const float r = rs[id] * inv_pool;
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
+                  for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
                 }
-                float dzs[8];
+                float dzs[CW];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) dzs[e] = dz[e] * lam_b_eff;
-                gmem_add8(accp + (size_t)id * p.bd + cm[it].boff, dzs);
+                for (int e = 0; e < CW; ++e) dzs[e] = dz[e] * lam_b_eff;
+                gmem_add4(accp + (size_t)id * p.bd + cm[it].boff, dzs);
               }
             }
           } else if (valid && MOT_BYTE_OK(it)) {
             const int id = idv[it];
             if (has_lam) {  // d lam_byte += <dz, bhat>
-              float b[8];
-              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              float b[CW];
+              V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
               const float r = rs[id];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) dlam_b += dz[e] * r * b[e];
+              for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
             }
             if (MODE == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) dz[e] *= lam_b_eff;
+              for (int e = 0; e < CW; ++e) dz[e] *= lam_b_eff;
             }
-            gmem_add8(accp + (size_t)id * p.bd + cm[it].boff, dz);
+            gmem_add4(accp + (size_t)id * p.bd + cm[it].boff, dz);
           }
         }
       }
       __syncwarp();  // shared-memory reads of this stage are done (values consumed above)
     }
-    // end of batch: at the end of a chunk the open row segment is flushed
-    if (chunk_last || m + 1 == n_batches || cntB == 0) {
-      if (has_tok && cur_v >= 0) {
-        const int b_end = chunk * p.R + p.R;
-        const bool trail = b_end < Ni && __ldg(p.stok + b_end) == cur_v;
-        flush(chunk, trail);
-        cur_v = -1;
-        seg_lead = false;
-      }
+    // at the end of a chunk the open row segment is flushed
+    if (chunk_last && has_tok && cur_v >= 0) {
+      const int b_end = chunk * p.R + p.R;
+      const bool trail = b_end < Ni && __ldg(p.stok + b_end) == cur_v;
+      flush(chunk, trail);
+      cur_v = -1;
+      seg_lead = false;
     }
     // advance: A <- B, prefetch the batch after
-    posA = posB; vA = vB; cntA = cntB;
+    A = B;
     if (iw == 1) iw = 0; else ik = 0;
-    load_batch(m + 2, posB, vB, cntB);
+    load_next(B);
   }
 
   // ---- lambda partials ----
@@ -985,17 +1008,23 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
-  const size_t smem = plan_smem(p, sizeof(T), kFwdThreads / 32, false, optin);
+  // widest CTA whose per-warp ring (>= 2 stages) fits next to the byte table: 32, 16 or 8 warps
+  int threads = kFwdThreads;
+  size_t smem = 0;
+  for (; threads >= 256; threads >>= 1) {
+    smem = plan_smem(p, sizeof(T), threads / 32, false, optin);
+    if (smem != 0 && (p.tab_smem || p.combine == MOT_TOK_ONLY || threads == 256)) break;
+  }
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
   if (MODE == 1 && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
   auto kern = mot_fwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   const long long warps_needed = p.N;
-  long long blocks = (warps_needed + (kFwdThreads / 32) - 1) / (kFwdThreads / 32);
+  long long blocks = (warps_needed + (threads / 32) - 1) / (threads / 32);
   if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   if (g_prof_fwd_start) cudaEventRecord(g_prof_fwd_start, s);
-  kern<<<(unsigned)blocks, kFwdThreads, smem, s>>>(p);
+  kern<<<(unsigned)blocks, threads, smem, s>>>(p);
   if (g_prof_fwd_stop) cudaEventRecord(g_prof_fwd_stop, s);
   count_launch();
   return check_launch();
