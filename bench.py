@@ -264,9 +264,11 @@ def run_ours(args):
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
     ws = torch.empty(ops.embed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
 
+    ops.embed_workspace_init(desc, ws)   # once; every completed backward leaves the workspace clean again
+
     def step():
         ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
-        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws)
+        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws, ws_clean=True)
         if world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
 
@@ -282,11 +284,6 @@ def run_ours(args):
 
     # ---- timed region: exactly K steps, device-timed, clocks sampled meanwhile ----
     K = args.steps
-    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for a, b in fwd_ev + bwd_ev:  # materialise the cudaEvent_t handles
-        a.record(); b.record()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -296,19 +293,31 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        lib.mot_profile_events(fwd_ev[i][0].cuda_event, fwd_ev[i][1].cuda_event, bwd_ev[i][0].cuda_event, bwd_ev[i][1].cuda_event)
         step()
     e1.record()
     barrier()
-    lib.mot_profile_events(None, None, None, None)
     launches = mot_b200.launch_count()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / K
     value = world * N / (ms_step * 1e-3)
+
+    # ---- instrumented pass (same K steps again, clocks still sampled): the library records CUDA event pairs on the
+    #      launch stream immediately around the main forward / backward kernel.  Kept out of the timed region above
+    #      because an event between two launches disables their programmatic-dependent-launch overlap. ----
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in fwd_ev + bwd_ev:  # materialise the cudaEvent_t handles
+        a.record(); b.record()
+    barrier()
+    for i in range(K):
+        lib.mot_profile_events(fwd_ev[i][0].cuda_event, fwd_ev[i][1].cuda_event, bwd_ev[i][0].cuda_event, bwd_ev[i][1].cuda_event)
+        step()
+    barrier()
+    lib.mot_profile_events(None, None, None, None)
+    clocks = sampler.stop() if rank == 0 else None
     fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / K
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / K
 
@@ -368,6 +377,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0, "traffic": None,
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms, "peak_source": peak_src,
+                         "timing": "CUDA event pairs around the kernel on its launch stream, averaged over a second "
+                                   "pass of the same K steps (events between launches would disable PDL overlap in the timed region)",
                          "fwd": {"achieved": A_fwd / (fwd_ms * 1e-3) / 1e9, "bytes": A_fwd, "ms": fwd_ms},
                          "bwd": {"achieved": A_bwd / (bwd_ms * 1e-3) / 1e9, "bytes": A_bwd, "ms": bwd_ms}},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MOT_B200_ABI_VERSION 1
+#define MOT_B200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 enum {
@@ -110,6 +110,15 @@ int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_v
 /* Workspace needed by mot_embed_bwd for this descriptor (bytes, 256-aligned). */
 size_t mot_embed_workspace_bytes(const MotDesc* d);
 
+/* State of a caller-owned workspace, passed as `ws_flags`.
+ *   MOT_WS_PLAN_READY : the workspace holds mot_embed_plan() for these tokens.
+ *   MOT_WS_CLEAN      : the head of the workspace (histogram, byte-gradient accumulators) is all zero, which is the
+ *                       state mot_embed_workspace_init() and every completed mot_embed_bwd() leave it in; a caller
+ *                       that keeps one workspace per stream passes it from the second step on and saves a memset.
+ *                       Without the flag the library clears what it needs itself. */
+enum { MOT_WS_PLAN_READY = 1, MOT_WS_CLEAN = 2 };
+int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_t ws_bytes, void* stream);
+
 /* Fused forward: out[n_tokens, out_dim] =
  *   f_out( combine( lam_tok * f_tok(E_tok[tok]),  lam_byte * f_byte(E_byte[byte ids]) ) ).
  * Replaces the embedding + mixin lines of GPT.forward (runs/71:312-314 + mixin_bytes :228-230 and
@@ -121,18 +130,19 @@ int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
                   const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream);
 
 /* Sort plan for the backward (token ids only; reusable by every table gathered with `tok`). */
-int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, void* stream);
+int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
+                   void* stream);
 
 /* Fused backward: the autograd graph of the lines above (rms_norm bwd, split, and the two
  * embedding_dense_backward scatter-adds).  gE_tok [tok_vocab, tok_dim] and gE_byte
  * [byte_vocab, byte_dim] are DENSE and fully overwritten (rows never gathered get zeros), so a
  * caller can all-reduce / feed them to the optimizer exactly like the reference's param.grad.
- *   g_lam : device float[2], overwritten (d lam_tok, d lam_byte), or NULL
- *   plan_ready != 0 : `workspace` already holds mot_embed_plan() for these tokens */
+ *   g_lam    : device float[2], overwritten (d lam_tok, d lam_byte), or NULL
+ *   ws_flags : MOT_WS_* state of `workspace`; on return the workspace is MOT_WS_CLEAN again */
 int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                   const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                   void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
-                  int32_t plan_ready, void* stream);
+                  int32_t ws_flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,12 +18,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "mot_b200", "libmot_b200.so")
-OBJ = os.path.join(HERE, "build")
+# experiment builds: MOT_LIB_SUFFIX=_x MOT_EXTRA_NVCC="-DFOO=1" python build.py -> mot_b200/libmot_b200_x.so (never shipped)
+SUFFIX = os.environ.get("MOT_LIB_SUFFIX", "")
+OUT = os.path.join(HERE, "mot_b200", f"libmot_b200{SUFFIX}.so")
+OBJ = os.path.join(HERE, "build" + SUFFIX)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-DNDEBUG", *(["-DMOT_EXPERIMENT_NO_RED"] if os.environ.get("MOT_EXPERIMENT_NO_RED") else []),
+    "-O3", "-lineinfo", "-std=c++17", "-DNDEBUG", *os.environ.get("MOT_EXTRA_NVCC", "").split(),
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]

@@ -7,6 +7,8 @@ namespace mot {
 // Backward plan: group positions by token id (counting sort over the vocabulary)
 // ======================================================================================
 __global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, int V, int* __restrict__ cnt) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
     atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
 }
@@ -19,6 +21,8 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
   __shared__ int wcarry[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int base = blockIdx.x * 1024;
+  pdl_launch_dependents();
+  pdl_wait();
   int carry = 0;
   for (int v = tid; v < base; v += 1024) carry += p.cnt[v];
 #pragma unroll
@@ -54,7 +58,10 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
 }
 
 // Scatter every position into its token's segment of the stream (cursor = cnt, counted back down to 0).
+// Leaves cnt all zero again (part of the self-cleaning workspace contract, MOT_WS_CLEAN).
 __global__ void plan_fill_kernel(EmbedParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.N) {
     const int v = clampi(p.tok[i], p.V - 1);
@@ -65,8 +72,13 @@ __global__ void plan_fill_kernel(EmbedParams p) {
   }
 }
 
-__global__ void mot_lam_store_kernel(const float* __restrict__ acc, float* __restrict__ g_lam) {
-  if (threadIdx.x < 2) g_lam[threadIdx.x] = acc[threadIdx.x];
+__global__ void mot_lam_store_kernel(float* __restrict__ acc, float* __restrict__ g_lam) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < 2) {
+    g_lam[threadIdx.x] = acc[threadIdx.x];
+    acc[threadIdx.x] = 0.f;  // self-cleaning workspace
+  }
 }
 
 // ======================================================================================
@@ -176,9 +188,9 @@ static int run_plan(const EmbedParams& p, cudaStream_t s) {
   if (p.combine == MOT_BYTES_ONLY || p.N == 0) return MOT_OK;
   long long hb = (p.N + 255) / 256;
   if (hb > 2048) hb = 2048;
-  plan_hist_kernel<<<(unsigned)hb, 256, 0, s>>>(p.tok, p.N, p.V, p.cnt);
-  plan_scan_kernel<<<(unsigned)((p.V + 1023) / 1024), 1024, 0, s>>>(p);
-  plan_fill_kernel<<<(unsigned)((p.N + 255) / 256), 256, 0, s>>>(p);
+  launch_pdl(plan_hist_kernel, dim3((unsigned)hb), dim3(256), 0, s, p.tok, p.N, p.V, p.cnt);
+  launch_pdl(plan_scan_kernel, dim3((unsigned)((p.V + 1023) / 1024)), dim3(1024), 0, s, p);
+  launch_pdl(plan_fill_kernel, dim3((unsigned)((p.N + 255) / 256)), dim3(256), 0, s, p);
   count_launch(3);
   return check_launch();
 }
@@ -213,7 +225,19 @@ extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* b
   return d->dtype == MOT_BF16 ? dispatch_fwd_bf16(p, s) : dispatch_fwd_f32(p, s);
 }
 
-extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, void* stream) {
+extern "C" int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_t ws_bytes, void* stream) {
+  if (int rc = validate(d)) return rc;
+  if (!workspace) return MOT_ERR_BAD_ARG;
+  EmbedParams p;
+  fill_params(d, p);
+  const WsLayout w = ws_layout(p);
+  if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
+  if (cudaMemsetAsync(workspace, 0, w.zero_end, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess) return check_launch();
+  return MOT_OK;
+}
+
+extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
+                              void* stream) {
   if (int rc = validate(d)) return rc;
   if (!workspace) return MOT_ERR_BAD_ARG;
   if (d->combine != MOT_BYTES_ONLY && !tok) return MOT_ERR_BAD_ARG;
@@ -225,15 +249,16 @@ extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* worksp
   bind_ws(p, w, workspace);
   p.tok = tok;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // zero cnt | byte_acc | lam_acc (contiguous at the head of the workspace)
-  if (cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
+  // zero cnt | byte_acc | lam_acc (contiguous at the head of the workspace) unless the caller vouches for it
+  if (!(ws_flags & MOT_WS_CLEAN) && cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
   return run_plan(p, s);
 }
 
 extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                              void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
-                             int32_t plan_ready, void* stream) {
+                             int32_t ws_flags, void* stream) {
+  const bool plan_ready = (ws_flags & MOT_WS_PLAN_READY) != 0, ws_clean = (ws_flags & MOT_WS_CLEAN) != 0;
   if (int rc = validate(d)) return rc;
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
   if (has_tok && !gE_tok) return MOT_ERR_BAD_ARG;
@@ -268,9 +293,9 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
   if (!plan_ready) {
-    if (cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
+    if (!ws_clean && cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
     if (int rc = run_plan(p, s)) return rc;
-  } else {  // plan kept from mot_embed_plan(): only the accumulators need clearing
+  } else if (!ws_clean) {  // plan kept from mot_embed_plan(): only the accumulators need clearing
     if (cudaMemsetAsync(reinterpret_cast<char*>(workspace) + w.byte_acc, 0, w.zero_end - w.byte_acc, s) != cudaSuccess)
       return check_launch();
   }
@@ -287,7 +312,7 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
   }
   if (rc) return rc;
   if ((d->flags & MOT_F_HAS_LAMBDAS) && g_lam) {
-    mot_lam_store_kernel<<<1, 32, 0, s>>>(p.lam_acc, g_lam);
+    launch_pdl(mot_lam_store_kernel, dim3(1), dim3(32), 0, s, p.lam_acc, g_lam);
     count_launch();
   }
   return check_launch();

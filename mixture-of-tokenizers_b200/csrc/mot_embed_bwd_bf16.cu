@@ -17,7 +17,7 @@ int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s) {
   return dispatch_bwd_wide_bf16(p, s);
 }
 int launch_finalize_bf16(const EmbedParams& p, int blocks, cudaStream_t s) {
-  mot_bwd_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p);
+  launch_pdl(mot_bwd_finalize_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, p);
   count_launch();
   return check_launch();
 }

@@ -12,7 +12,7 @@ int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s) {
   return dispatch_bwd_wide_f32(p, s);
 }
 int launch_finalize_f32(const EmbedParams& p, int blocks, cudaStream_t s) {
-  mot_bwd_finalize_kernel<float><<<blocks, 256, 0, s>>>(p);
+  launch_pdl(mot_bwd_finalize_kernel<float>, dim3(blocks), dim3(256), 0, s, p);
   count_launch();
   return check_launch();
 }

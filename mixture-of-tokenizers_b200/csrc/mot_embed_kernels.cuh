@@ -25,8 +25,10 @@
 namespace mot {
 
 constexpr int kFwdThreads = 1024;
-constexpr int kBwdThreads = 384;
-constexpr int kMaxStages = 8;
+#ifndef MOT_BWD_THREADS
+#define MOT_BWD_THREADS 384
+#endif
+constexpr int kBwdThreads = MOT_BWD_THREADS;
 constexpr int kByteRep = 16;  // replicas of the fp32 byte-grad accumulator (spreads hot byte ids over L2 atomic units)
 
 struct EmbedParams {
@@ -178,6 +180,8 @@ inline int pick_mode(const EmbedParams& p, int cw) {
 
 #define MOT_TOK_OK(it) (MODE == 1 || cm[it].toff >= 0)
 #define MOT_BYTE_OK(it) (MODE == 1 || cm[it].slot >= 0)
+// element offset of chunk `it` in the token row: affine (base + immediate addressing) on the fast path
+#define MOT_TOFF(it) (MODE == 1 ? ((it) * 32 + lane) * CW : cm[it].toff)
 #define MOT_CHUNK_OK(it) (MODE == 1 || ((it) * 32 + lane) * CW < p.Do)
 
 template <typename T, int MODE = 0, int CW = 8>
@@ -282,7 +286,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
   if (lane == 0)
     for (int s = 0; s < D; ++s) mbar_init(bars + s, 1);
   fence_mbar_init();
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();  // nothing above touches global memory
 
   const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs: every SM gets the same share +-1
                                                  // (n_tokens < 2^31, validated on the host: 32-bit position math)
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (MOT_TOK_OK(it)) {
-          Vec8<T>::unpack(Vec8<T>::lds_raw(trow + cm[it].toff), x[it]);
+          Vec8<T>::unpack(Vec8<T>::lds_raw(trow + MOT_TOFF(it)), x[it]);
           if (tok_norm) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) ss_t += x[it][e] * x[it][e];
@@ -445,6 +451,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
   using C = Cfg<MODE>;
   constexpr int CW = kBwdCW;
   using V = Vec<T, CW>;
+  const int lane = lane_id();
   const bool tok_norm = C::tok_norm(p);
   const bool need_t = tok_norm || C::has_lam(p);
   float dot = 0.f, ss = 0.f;  // <Du, tv>, |tv|^2
@@ -453,7 +460,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
     for (int it = 0; it < CPL; ++it) {
       if (MOT_TOK_OK(it)) {
         float tv[CW];
-        V::unpack(V::lds_raw(trow_smem + cm[it].toff), tv);
+        V::unpack(V::lds_raw(trow_smem + MOT_TOFF(it)), tv);
 #pragma unroll
         for (int e = 0; e < CW; ++e) {
           dot += Du[it][e] * tv[e];
@@ -474,7 +481,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
       float o[CW];
       if (tok_norm) {
         float tv[CW];
-        V::unpack(V::lds_raw(trow_smem + cm[it].toff), tv);
+        V::unpack(V::lds_raw(trow_smem + MOT_TOFF(it)), tv);
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e] - b * tv[e];
       } else if (MODE == 0) {
@@ -484,7 +491,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = Du[it][e];
       }
-      V::stg(grow + cm[it].toff, o);
+      V::stg(grow + MOT_TOFF(it), o);
     }
   }
   return r_t * dot;
@@ -519,7 +526,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   if (lane == 0)
     for (int s = 0; s < D; ++s) mbar_init(bars + s, 1);
   fence_mbar_init();
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();  // nothing above touches global memory
 
   const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs
   const int W = gridDim.x * nw;
@@ -657,7 +666,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (MOT_TOK_OK(it))
-          *reinterpret_cast<float4*>(prow + cm[it].toff) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
+          *reinterpret_cast<float4*>(prow + MOT_TOFF(it)) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
       }
     }
 #pragma unroll
@@ -704,7 +713,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         for (int it = 0; it < CPL; ++it) {
           if (MOT_TOK_OK(it)) {
             float tv[CW];
-            V::unpack(V::lds_raw(trow + cm[it].toff), tv);
+            V::unpack(V::lds_raw(trow + MOT_TOFF(it)), tv);
 #pragma unroll
             for (int e = 0; e < CW; ++e) ss_t += tv[e] * tv[e];
           }
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (has_tok && MOT_TOK_OK(it)) {
-          V::unpack(V::lds_raw(trow + cm[it].toff), z[it]);
+          V::unpack(V::lds_raw(trow + MOT_TOFF(it)), z[it]);
           if (MODE == 0) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) z[it][e] *= tscale;
@@ -862,6 +871,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 // byte-norm backward, cast; (c) lambda partials of (a).
 template <typename T>
 __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = lane_id();
   const int nw = blockDim.x >> 5;
   const int gw = blockIdx.x * nw + (threadIdx.x >> 5);
@@ -950,6 +961,13 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
             x[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride);
             y[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride + 4);
           }
+          // leave the accumulators zeroed for the next call (the workspace cleans itself, see MOT_WS_CLEAN)
+          float* dst = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+#pragma unroll
+          for (int rep = 0; rep < kByteRep; ++rep) {
+            *reinterpret_cast<float4*>(dst + rep * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + rep * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int rep = 0; rep < kByteRep; ++rep) {
             a[0] += x[rep].x; a[1] += x[rep].y; a[2] += x[rep].z; a[3] += x[rep].w;
@@ -990,7 +1008,7 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
 // Pick the ring depth and whether the byte table fits next to it; returns dynamic smem bytes or 0.
 inline size_t plan_smem(EmbedParams& p, size_t esz, int warps, bool backward, int optin) {
   static const char* env_st = getenv("MOT_STAGES");  // debug knob
-  const int want = env_st ? atoi(env_st) : 4;
+  const int want = env_st ? atoi(env_st) : 2;  // measured: 2 stages per warp are as fast as 4 (gpurun_out/exp3.log)
   p.tab_smem = 1;
   for (int tab = 1; tab >= 0; --tab) {
     p.tab_smem = tab;
@@ -1009,9 +1027,10 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
   // widest CTA whose per-warp ring (>= 2 stages) fits next to the byte table: 32, 16 or 8 warps
-  int threads = kFwdThreads;
+  static const char* env_thr = getenv("MOT_FWD_THREADS");  // debug knob
+  int threads = env_thr ? atoi(env_thr) : kFwdThreads;
   size_t smem = 0;
-  for (; threads >= 256; threads >>= 1) {
+  for (; threads >= 256; threads = threads > 512 ? threads - 256 : threads >> 1) {
     smem = plan_smem(p, sizeof(T), threads / 32, false, optin);
     if (smem != 0 && (p.tab_smem || p.combine == MOT_TOK_ONLY || threads == 256)) break;
   }
@@ -1024,7 +1043,7 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   if (blocks > sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   if (g_prof_fwd_start) cudaEventRecord(g_prof_fwd_start, s);
-  kern<<<(unsigned)blocks, threads, smem, s>>>(p);
+  launch_pdl(kern, dim3((unsigned)blocks), dim3(threads), smem, s, p);
   if (g_prof_fwd_stop) cudaEventRecord(g_prof_fwd_stop, s);
   count_launch();
   return check_launch();
@@ -1041,7 +1060,7 @@ static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
-  kern<<<(unsigned)sms, kBwdThreads, smem, s>>>(p);
+  launch_pdl(kern, dim3((unsigned)sms), dim3(kBwdThreads), smem, s, p);
   if (g_prof_stop) cudaEventRecord(g_prof_stop, s);
   count_launch();
   return check_launch();

@@ -11,9 +11,9 @@ import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmot_b200.so")
+LIB_PATH = os.path.join(_HERE, "libmot_b200" + os.environ.get("MOT_LIB_SUFFIX", "") + ".so")  # suffix: experiment builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 # enums of include/mot_b200.h
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_MISALIGNED, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = range(7)
 BF16, F32 = 0, 1
@@ -21,6 +21,7 @@ TTB_I16, TTB_F32, TTB_BF16 = 0, 1, 2
 ADD, CONCAT, TOK_ONLY, BYTES_ONLY, MEAN = range(5)
 F_TOK_NORM, F_BYTE_NORM, F_OUT_NORM, F_BYTES_FIRST = 1, 2, 4, 8
 F_SLOT_MAJOR, F_IDS_FROM_TTB, F_TTB_SCRAMBLE, F_IDS_I64, F_HAS_LAMBDAS = 16, 32, 64, 128, 256
+WS_PLAN_READY, WS_CLEAN = 1, 2
 
 
 class MotDesc(C.Structure):
@@ -45,7 +46,8 @@ _SIGNATURES = {
     "mot_ttb_expand": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "mot_embed_workspace_bytes": (C.c_size_t, [C.POINTER(MotDesc)]),
     "mot_embed_fwd": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mot_embed_plan": (C.c_int, [C.POINTER(MotDesc), _P, _P, C.c_size_t, _P]),
+    "mot_embed_workspace_init": (C.c_int, [C.POINTER(MotDesc), _P, C.c_size_t, _P]),
+    "mot_embed_plan": (C.c_int, [C.POINTER(MotDesc), _P, _P, C.c_size_t, C.c_int32, _P]),
     "mot_embed_bwd": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                 C.c_int32, _P]),
 }

@@ -126,22 +126,60 @@ def embed_workspace_bytes(desc: L.MotDesc) -> int:
     return int(L.lib().mot_embed_workspace_bytes(desc))
 
 
-def embed_plan(desc: L.MotDesc, tok, ws) -> None:
+def embed_workspace_init(desc: L.MotDesc, ws) -> None:
+    """Zero the head of a fresh workspace once; afterwards every completed backward leaves it clean (MOT_WS_CLEAN)."""
     dev = ws.device
     with torch.cuda.device(dev):
-        rc = L.lib().mot_embed_plan(desc, _ptr(tok), _ptr(ws), ws.numel(), _stream(dev))
+        rc = L.lib().mot_embed_workspace_init(desc, _ptr(ws), ws.numel(), _stream(dev))
+    L.check(rc, "mot_embed_workspace_init")
+
+
+def embed_plan(desc: L.MotDesc, tok, ws, ws_clean: bool = False) -> None:
+    dev = ws.device
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_embed_plan(desc, _ptr(tok), _ptr(ws), ws.numel(), L.WS_CLEAN if ws_clean else 0, _stream(dev))
     L.check(rc, "mot_embed_plan")
 
 
 def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
-                       plan_ready: bool = False) -> None:
-    """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten."""
+                       plan_ready: bool = False, ws_clean: bool = False) -> None:
+    """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten.  `ws_clean`: the caller
+    vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward)."""
     dev = grad_out.device
+    flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0)
     with torch.cuda.device(dev):
         rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
                                    _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
-                                   1 if plan_ready else 0, _stream(dev))
+                                   flags, _stream(dev))
     L.check(rc, "mot_embed_bwd")
+
+
+class Workspace:
+    """A backward workspace kept across steps on one stream, remembering whether the library left it clean (so the
+    steady-state step needs no memset).  One instance per (device, stream, table geometry)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.clean = False
+
+    def reserve(self, desc: L.MotDesc, dev) -> torch.Tensor:
+        need = embed_workspace_bytes(desc)
+        if self.buf is None or self.buf.numel() < need or self.buf.device != dev:
+            self.buf = torch.empty(need, dtype=torch.uint8, device=dev)
+            self.clean = False
+        return self.buf
+
+
+_WS_CACHE: dict = {}
+
+
+def cached_workspace(desc: L.MotDesc, dev) -> Workspace:
+    # the zeroed head of the workspace is laid out by (tok_vocab, byte_vocab, byte_dim): one workspace per geometry
+    key = (dev.index, _stream(dev), desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        ws = _WS_CACHE[key] = Workspace()
+    return ws
 
 
 class _MotEmbedFn(torch.autograd.Function):
@@ -187,8 +225,11 @@ class _MotEmbedFn(torch.autograd.Function):
         gE_tok = torch.empty_like(E_tok) if E_tok is not None else None
         gE_byte = torch.empty_like(E_byte) if E_byte is not None else None
         g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
-        ws = torch.empty(embed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
-        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws)
+        ws = cached_workspace(desc, dev)
+        buf = ws.reserve(desc, dev)
+        clean, ws.clean = ws.clean, False   # stays False if the call raises
+        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, buf, ws_clean=clean)
+        ws.clean = True
         if g_lam is not None:
             g_lam = g_lam.to(ctx.lam_dtype)
         return None, None, None, None, None, None, gE_tok, gE_byte, g_lam

@@ -49,7 +49,7 @@ def test_strerror_and_codes():
 
 
 def desc(**kw):
-    base = dict(abi_version=1, dtype=L.BF16, n_tokens=49152, seq_len=0, tok_vocab=50257, byte_vocab=458, bpt=16,
+    base = dict(abi_version=L.ABI_VERSION, dtype=L.BF16, n_tokens=49152, seq_len=0, tok_vocab=50257, byte_vocab=458, bpt=16,
                 tok_dim=768, byte_dim=48, out_dim=768, combine=L.ADD, flags=L.F_OUT_NORM, ttb_dtype=0, eps=1e-7)
     base.update(kw)
     return L.MotDesc(**base)
