@@ -262,13 +262,18 @@ def run_ours(args):
     gE_tok, gE_byte = flat[:n_tok_g].view(V_TOK, Dt), flat[n_tok_g:].view(V_BYTE, bd)
     g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
-    ws = torch.empty(ops.embed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
-
-    ops.embed_workspace_init(desc, ws)   # once; every completed backward leaves the workspace clean again
+    ws = ops.acquire_workspace(desc, dev)   # kept across steps: every completed backward leaves it clean (no memset)
+    main_stream = torch.cuda.current_stream(dev)
 
     def step():
+        # the same call sequence as mot_b200.mot_embed + autograd: the backward plan (counting sort of the token ids)
+        # is launched on a side stream beside the forward kernel, the backward waits for it
+        ev = ops.embed_plan_async(desc, tok, ws, dev)
         ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
-        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws, ws_clean=True)
+        main_stream.wait_event(ev)
+        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf,
+                               plan_ready=True, ws_clean=True)
+        ws.clean = True
         if world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
 

@@ -13,23 +13,31 @@ __global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, i
     atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
 }
 
-// Exclusive scan of the histogram -> segment offsets.  One CTA per 1024-entry tile: each CTA first sums every
-// entry in front of its tile (coalesced, <= 49 independent loads per thread, all L2 hits), then scans its own
-// tile with warp shuffles.
-__global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
-  __shared__ int wsum[32];
-  __shared__ int wcarry[32];
+// Exclusive scan of the histogram -> segment offsets.  One 256-thread CTA per 1024-entry tile (four entries per
+// thread): each CTA first sums every entry in front of its tile (coalesced 16-byte loads, all L2 hits), then scans
+// its own tile with warp shuffles.  Small CTAs with few registers so that the plan can run beside the forward
+// kernel on a second stream.
+constexpr int kScanTile = 1024;
+__global__ void __launch_bounds__(256) plan_scan_kernel(EmbedParams p) {
+  __shared__ int wsum[8];
+  __shared__ int wcarry[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int base = blockIdx.x * 1024;
+  const int base = blockIdx.x * kScanTile;  // multiple of 4: the tile starts 16-byte aligned
   pdl_launch_dependents();
   pdl_wait();
   int carry = 0;
-  for (int v = tid; v < base; v += 1024) carry += p.cnt[v];
+  for (int v = tid * 4; v < base; v += 256 * 4) {
+    const int4 c = *reinterpret_cast<const int4*>(p.cnt + v);
+    carry += c.x + c.y + c.z + c.w;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, o);
   if (lane == 0) wcarry[warp] = carry;
-  const int v = base + tid;
-  const int mine = v < p.V ? p.cnt[v] : 0;
+  const int v0 = base + tid * 4;
+  int c[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c[j] = v0 + j < p.V ? p.cnt[v0 + j] : 0;
+  const int mine = c[0] + c[1] + c[2] + c[3];
   int inc = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -39,22 +47,26 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(EmbedParams p) {
   if (lane == 31) wsum[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int c = wcarry[lane];
+    int cr = lane < 8 ? wcarry[lane] : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    const int w = wsum[lane];
+    for (int o = 16; o > 0; o >>= 1) cr += __shfl_xor_sync(0xffffffffu, cr, o);
+    const int w = lane < 8 ? wsum[lane] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, wi, o);
       if (lane >= o) wi += t;
     }
-    wsum[lane] = c + wi - w;  // exclusive warp offset including the carry-in
+    if (lane < 8) wsum[lane] = cr + wi - w;  // exclusive warp offset including the carry-in
   }
   __syncthreads();
-  const int ex = wsum[warp] + inc - mine;
-  if (v < p.V) p.off[v] = ex;
-  if (v == p.V - 1) p.off[p.V] = ex + mine;
+  int ex = wsum[warp] + inc - mine;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (v0 + j < p.V) p.off[v0 + j] = ex;
+    ex += c[j];
+    if (v0 + j == p.V - 1) p.off[p.V] = ex;
+  }
 }
 
 // Scatter every position into its token's segment of the stream (cursor = cnt, counted back down to 0).
@@ -189,7 +201,7 @@ static int run_plan(const EmbedParams& p, cudaStream_t s) {
   long long hb = (p.N + 255) / 256;
   if (hb > 2048) hb = 2048;
   launch_pdl(plan_hist_kernel, dim3((unsigned)hb), dim3(256), 0, s, p.tok, p.N, p.V, p.cnt);
-  launch_pdl(plan_scan_kernel, dim3((unsigned)((p.V + 1023) / 1024)), dim3(1024), 0, s, p);
+  launch_pdl(plan_scan_kernel, dim3((unsigned)((p.V + kScanTile - 1) / kScanTile)), dim3(256), 0, s, p);
   launch_pdl(plan_fill_kernel, dim3((unsigned)((p.N + 255) / 256)), dim3(256), 0, s, p);
   count_launch(3);
   return check_launch();

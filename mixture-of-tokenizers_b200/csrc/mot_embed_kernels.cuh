@@ -24,7 +24,9 @@
 
 namespace mot {
 
-constexpr int kFwdThreads = 1024;
+// forward CTA: compiled for up to 1024 threads (<= 64 registers), launched with 24 warps, which leaves a quarter of the
+// register file to kernels on other streams (the backward plan runs beside the forward)
+constexpr int kFwdThreads = 768;
 #ifndef MOT_BWD_THREADS
 #define MOT_BWD_THREADS 384
 #endif
@@ -266,7 +268,7 @@ __device__ __forceinline__ void gmem_add4(float* a, const float (&v)[4]) {
 // Forward
 // ======================================================================================
 template <typename T, int CPL, int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 1) mot_fwd_kernel(const EmbedParams p) {
+__global__ void __launch_bounds__(1024, 1) mot_fwd_kernel(const EmbedParams p) {
   using C = Cfg<MODE>;
   constexpr int CW = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -155,10 +155,11 @@ def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_
 
 
 class Workspace:
-    """A backward workspace kept across steps on one stream, remembering whether the library left it clean (so the
-    steady-state step needs no memset).  One instance per (device, stream, table geometry)."""
+    """A backward workspace that remembers whether the library left it clean (so the steady-state step needs no
+    memset).  Instances are recycled through a pool per (device, table geometry)."""
 
-    def __init__(self):
+    def __init__(self, key):
+        self.key = key
         self.buf: Optional[torch.Tensor] = None
         self.clean = False
 
@@ -170,16 +171,45 @@ class Workspace:
         return self.buf
 
 
-_WS_CACHE: dict = {}
+_WS_POOL: dict = {}
+_SIDE_STREAMS: dict = {}
 
 
-def cached_workspace(desc: L.MotDesc, dev) -> Workspace:
-    # the zeroed head of the workspace is laid out by (tok_vocab, byte_vocab, byte_dim): one workspace per geometry
-    key = (dev.index, _stream(dev), desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine)
-    ws = _WS_CACHE.get(key)
-    if ws is None:
-        ws = _WS_CACHE[key] = Workspace()
+def acquire_workspace(desc: L.MotDesc, dev) -> Workspace:
+    # the zeroed head of the workspace is laid out by (tok_vocab, byte_vocab, byte_dim): one pool per geometry
+    key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine)
+    free = _WS_POOL.setdefault(key, [])
+    ws = free.pop() if free else Workspace(key)
+    ws.reserve(desc, dev)
     return ws
+
+
+def release_workspace(ws: Workspace) -> None:
+    free = _WS_POOL.setdefault(ws.key, [])
+    if len(free) < 4:
+        free.append(ws)
+
+
+def side_stream(dev) -> torch.cuda.Stream:
+    """Per-device stream on which the backward plan (a counting sort of the token ids) runs beside the forward."""
+    st = _SIDE_STREAMS.get(dev.index)
+    if st is None:
+        st = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def embed_plan_async(desc: L.MotDesc, tok, ws: Workspace, dev) -> torch.cuda.Event:
+    """Launch the plan on the side stream, ordered after the work already queued on the current stream; returns the
+    event the backward has to wait for."""
+    cur = torch.cuda.current_stream(dev)
+    side = side_stream(dev)
+    side.wait_stream(cur)
+    clean, ws.clean = ws.clean, False
+    with torch.cuda.stream(side):
+        embed_plan(desc, tok, ws.buf, ws_clean=clean)
+        ev = side.record_event()
+    ws.buf.record_stream(side)
+    return ev
 
 
 class _MotEmbedFn(torch.autograd.Function):
@@ -207,6 +237,12 @@ class _MotEmbedFn(torch.autograd.Function):
         desc = make_desc(spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=ttb, has_lam=lam is not None, seq_len=seq_len)
         ref = E_tok_c if E_tok_c is not None else E_byte_c
         out = torch.empty((n, desc.out_dim), dtype=ref.dtype, device=dev)
+        # the backward needs the positions grouped by token id: start that sort now, beside the forward kernel
+        ctx.ws, ctx.plan_event = None, None
+        needs_grad = any(ctx.needs_input_grad[6:9])   # E_tok, E_byte, lam
+        if needs_grad and tok is not None and n > 0:
+            ctx.ws = acquire_workspace(desc, dev)
+            ctx.plan_event = embed_plan_async(desc, tok, ctx.ws, dev)
         embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out)
         ctx.desc, ctx.dev = desc, dev
         ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)])
@@ -225,11 +261,19 @@ class _MotEmbedFn(torch.autograd.Function):
         gE_tok = torch.empty_like(E_tok) if E_tok is not None else None
         gE_byte = torch.empty_like(E_byte) if E_byte is not None else None
         g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
-        ws = cached_workspace(desc, dev)
-        buf = ws.reserve(desc, dev)
-        clean, ws.clean = ws.clean, False   # stays False if the call raises
-        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, buf, ws_clean=clean)
-        ws.clean = True
+        ws, planned = ctx.ws, ctx.plan_event is not None
+        if ws is None:
+            ws = acquire_workspace(desc, dev)
+        if planned:
+            torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+            clean = True          # the plan ran on a clean (or freshly cleared) workspace and leaves it clean
+        else:
+            clean, ws.clean = ws.clean, False
+        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
+                           plan_ready=planned, ws_clean=clean)
+        ws.clean = True           # every completed backward leaves the head of the workspace zeroed
+        ctx.ws = ctx.plan_event = None
+        release_workspace(ws)
         if g_lam is not None:
             g_lam = g_lam.to(ctx.lam_dtype)
         return None, None, None, None, None, None, gE_tok, gE_byte, g_lam

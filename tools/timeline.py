@@ -27,13 +27,14 @@ out = torch.empty(N, Do, dtype=dt, device=d)
 gE_tok, gE_byte = torch.empty_like(E_tok), torch.empty_like(E_byte)
 g_lam = torch.empty(2, device=d) if lam is not None else None
 desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
-ws = torch.empty(ops.embed_workspace_bytes(desc), dtype=torch.uint8, device=d)
-step = bench.make_step(desc, tok, ids, E_tok, E_byte, lam, out, gout, gE_tok, gE_byte, g_lam, ws) if hasattr(bench, "make_step") else None
-if step is None:
-    def step():
-        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
-        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws, ws_clean=True)
-ops.embed_workspace_init(desc, ws)
+ws = ops.acquire_workspace(desc, d)
+main_stream = torch.cuda.current_stream(d)
+def step():
+    ev = ops.embed_plan_async(desc, tok, ws, d)
+    ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
+    main_stream.wait_event(ev)
+    ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf, plan_ready=True, ws_clean=True)
+    ws.clean = True
 for _ in range(10):
     step()
 torch.cuda.synchronize()
