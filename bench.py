@@ -145,6 +145,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -380,7 +388,8 @@ def run_ours(args):
             "kernel_ms": {"fwd": fwd_ms, "bwd_main": bwd_ms},
             "step_hbm_gbs": (A_fwd + A_bwd) / (ms_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0, "traffic": None,
+                         "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0,
+                         "traffic": measured_traffic(w["name"], dom),
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms, "peak_source": peak_src,
                          "timing": "CUDA event pairs around the kernel on its launch stream, averaged over a second "
                                    "pass of the same K steps (events between launches would disable PDL overlap in the timed region)",
