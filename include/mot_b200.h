@@ -144,6 +144,29 @@ int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
                   void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                   int32_t ws_flags, void* stream);
 
+/* ---- dense projection of the concat+projection variants (tcgen05 tensor cores) -------------------------------
+ * bf16 operands, fp32 accumulation in tensor memory.  in_dim = tok_dim + bpt*byte_dim (the row width of the
+ * [tok | bytes] operand mot_embed_fwd produces with MOT_CONCAT), out_dim = model_dim; both multiples of 8. */
+
+/* y[n_tokens, out_dim] = x[n_tokens, in_dim] . w[out_dim, in_dim]^T (+ bias[out_dim], fp32, or NULL).
+ * Replaces F.linear of mixin_bytes (runs/7:233-234), CastedLinear (spt/train_gpt.py:185-186,443) and
+ * DigitMixinConcat.fc (mathblations/model.py:261,268).  y is bf16, or fp32 when y_f32 != 0. */
+int mot_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t n_tokens, int32_t in_dim,
+                   int32_t out_dim, int32_t y_f32, void* stream);
+/* dx[n_tokens, in_dim] = dy[n_tokens, out_dim] . w[out_dim, in_dim]   (autograd of F.linear w.r.t. its input) */
+int mot_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t n_tokens, int32_t in_dim, int32_t out_dim,
+                         void* stream);
+/* dw[out_dim, in_dim] = dy^T . x, reduced in fp32 into dw_f32 (overwritten; the fp32 master-weight gradient of
+ * spt/train_gpt.py:1155-1156) and, when dw_bf16 != NULL, also cast to bf16 (the bf16 mixin weight of runs/7:249). */
+int mot_linear_bwd_weight(const void* dy, const void* x, float* dw_f32, void* dw_bf16, int64_t n_tokens, int32_t in_dim,
+                          int32_t out_dim, void* stream);
+
+/* Row-wise rms_norm without weight (F.rms_norm(x, (x.size(-1),)), spt/train_gpt.py:172-173) over [n_rows, dim] and
+ * its backward dy = rs*g - y*rs^3*mean(g.y): the `norm(...)` around the projection (runs/7:234, train_gpt.py:443). */
+int mot_rmsnorm_fwd(const void* y, void* out, int64_t n_rows, int32_t dim, int32_t dtype, float eps, void* stream);
+int mot_rmsnorm_bwd(const void* y, const void* grad_out, void* dy, int64_t n_rows, int32_t dim, int32_t dtype, float eps,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
