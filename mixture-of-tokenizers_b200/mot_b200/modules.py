@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .ops import MixSpec, mot_embed
+from .ops import MixSpec, mot_embed, mot_embed_proj
 
 # variant name -> MixSpec kwargs (`slot_major` is the `.view(bpt,-1)` id layout of the sum runs)
 RUN_VARIANTS = {
@@ -64,3 +64,92 @@ class MoTEmbedding(nn.Module):
                       spec, bpt=self.bpt, lam=lam, ttb=self.ttb if byte_inputs is None else None,
                       seq_len=token_inputs.numel())
         return x[None]
+
+
+# variant name -> MixSpec kwargs of the concat + dense projection family
+PROJ_VARIANTS = {
+    "V1": dict(combine="concat", tok_norm=True, byte_norm=True, out_norm=True),                  # runs/7:226-234,317-319
+    "V2": dict(combine="concat", tok_norm=False, byte_norm=False, out_norm=True, slot_major=True),  # runs/72:227-230,313-315
+}
+
+
+def _init_linear_(w: torch.Tensor) -> torch.Tensor:
+    """CastedLinear.reset_parameters (spt/train_gpt.py:179-183): uniform +-sqrt(3)*0.5*in^-0.5."""
+    bound = (3 ** 0.5) * 0.5 * (w.shape[1] ** -0.5)
+    with torch.no_grad():
+        return w.uniform_(-bound, bound)
+
+
+class MoTProjEmbedding(nn.Module):
+    """The concat + projection front of the modded-nanogpt runs (runs/7, 72, 75-79): parameters `embed_tokens.weight`,
+    `embed_bytes.weight`, `byte_mixin_weight` [model_dim, token_dim + bpt*byte_dim] (bf16 like runs/7:249).
+    forward(token_inputs [T] int32, byte_inputs int32 [1, T*bpt] (V1) or [bpt, T] (V2)) -> [1, T, model_dim]:
+    fused gather of the [tok | bytes] operand, tcgen05 projection, rms_norm."""
+
+    def __init__(self, token_vocab_size: int, byte_vocab_size: int, token_dim: int, byte_dim: int, model_dim: int,
+                 bytes_per_token: int = 16, variant: str = "V1"):
+        super().__init__()
+        if variant not in PROJ_VARIANTS:
+            raise NotImplementedError(f"mot_b200: projection variant {variant!r} has no fused kernel")
+        self.variant, self.bpt = variant, bytes_per_token
+        self.spec = MixSpec(**PROJ_VARIANTS[variant])
+        self.embed_tokens = nn.Embedding(token_vocab_size, token_dim)
+        self.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim)
+        self.byte_mixin_weight = nn.Parameter(
+            _init_linear_(torch.empty(model_dim, token_dim + bytes_per_token * byte_dim)).bfloat16())
+
+    def forward(self, token_inputs: torch.Tensor, byte_inputs: torch.Tensor) -> torch.Tensor:
+        assert token_inputs.ndim == 1  # runs/7:305
+        x = mot_embed_proj(token_inputs, byte_inputs, self.embed_tokens.weight, self.embed_bytes.weight,
+                           self.byte_mixin_weight, self.spec, bpt=self.bpt)
+        return x[None]
+
+
+class _Holder(nn.Module):
+    """Parameter container that only exists to reproduce the reference's state-dict keys."""
+
+
+class SptByteMixEmbedding(nn.Module):
+    """scaled-pre-train's `FlexibleEmbedding` + `ByteMixin(concat)` pair (spt/train_gpt.py:327-379,430-443,560-565)
+    fused behind the same call: forward(tokens [B,S] int32, byte_tensor [B,S*bpt] int64 | None,
+    byte_tensor_pulled [B,S*bpt] int64 | None) -> x [B,S,model_dim], the value `self.byte_mixin(*self.embed(...))`
+    has at spt/train_gpt.py:605-606.  State-dict keys match the reference: `embed.embed_tokens.weight`,
+    `embed.embed_bytes.weight`, `byte_mixin.mixin.mixin.weight` (fp32 master, cast to bf16 per call like
+    CastedLinear, gradient returned in fp32).  byte_mixin_method "noop" gives norm(embed_tokens(tokens)).
+    Refused (no fallback): cross_attn, byte self-attention, add_padded_and_pulled."""
+
+    def __init__(self, vocab_size: int, byte_vocab_size: int, token_dim: int, byte_dim: int, model_dim: int,
+                 bytes_per_token: int = 16, byte_mixin_method: str = "concat", pull_in: bool = True,
+                 add_padded_and_pulled: bool = False, use_byte_self_attn: bool = False):
+        super().__init__()
+        if byte_mixin_method not in ("concat", "noop"):
+            raise NotImplementedError(f"mot_b200: byte_mixin_method={byte_mixin_method!r} is attention pooling, "
+                                      "not a gather/pool; it has no kernel here (no fallback)")
+        if use_byte_self_attn:
+            raise NotImplementedError("mot_b200: use_byte_self_attn=True is not supported (no fallback)")
+        if add_padded_and_pulled:
+            raise NotImplementedError("mot_b200: add_padded_and_pulled (spt/train_gpt.py:371-379) is not supported yet")
+        self.method, self.bpt, self.pull_in = byte_mixin_method, bytes_per_token, pull_in
+        self.embed = _Holder()
+        self.embed.embed_tokens = nn.Embedding(vocab_size, token_dim if byte_mixin_method != "noop" else model_dim)
+        self.byte_mixin = _Holder()
+        if byte_mixin_method == "concat":
+            self.embed.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim)
+            self.byte_mixin.mixin = _Holder()
+            self.byte_mixin.mixin.mixin = _Holder()
+            self.byte_mixin.mixin.mixin.weight = nn.Parameter(
+                _init_linear_(torch.empty(model_dim, token_dim + bytes_per_token * byte_dim)))
+        self.spec = MixSpec(combine="concat", tok_norm=True, byte_norm=True, out_norm=True)
+
+    def forward(self, tokens: torch.Tensor, byte_tensor: Optional[torch.Tensor] = None,
+                byte_tensor_pulled: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, S = tokens.shape
+        if self.method == "noop":   # _forward_tokens, :342-348
+            x = mot_embed(tokens, None, self.embed.embed_tokens.weight, None, MixSpec(combine="tok_only"))
+            return x.view(B, S, -1)
+        ids = byte_tensor_pulled if self.pull_in else byte_tensor   # _forward_bytes_pulled / _padded, :350-369
+        if ids is None:
+            raise RuntimeError("mot_b200: byte ids are required (byte_tensor_pulled with pull_in, else byte_tensor)")
+        x = mot_embed_proj(tokens, ids, self.embed.embed_tokens.weight, self.embed.embed_bytes.weight,
+                           self.byte_mixin.mixin.mixin.weight, self.spec, bpt=self.bpt)
+        return x.view(B, S, -1)

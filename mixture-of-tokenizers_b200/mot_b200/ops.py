@@ -290,6 +290,152 @@ def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], 
     return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# concat + dense projection variants (V1 runs/7:226-234,317-319 and spt/train_gpt.py:439-443; V2 runs/72:227-230)
+# ------------------------------------------------------------------------------------------------------------
+def _check_bf16(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.bfloat16:
+            raise NotImplementedError("mot_b200: the tcgen05 projection kernels take bf16 operands "
+                                      f"(got {t.dtype}); fp32 tables are not supported on this path")
+
+
+def linear_forward_out(x, w, y, bias=None) -> None:
+    """y[n, Do] = x[n, K] . w[Do, K]^T (+ bias): mot_linear_fwd (tcgen05).  y is bf16 or fp32."""
+    _check_bf16(x, w)
+    dev = _require_cuda(x, w, y, bias)
+    n, K = x.shape
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, K, w.shape[0],
+                                    1 if y.dtype == torch.float32 else 0, _stream(dev))
+    L.check(rc, "mot_linear_fwd")
+
+
+def linear_bwd_input_out(dy, w, dx) -> None:
+    """dx[n, K] = dy[n, Do] . w[Do, K]: mot_linear_bwd_input (w read in place as an MN-major operand)."""
+    _check_bf16(dy, w, dx)
+    dev = _require_cuda(dy, w, dx)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_linear_bwd_input(_ptr(dy), _ptr(w), _ptr(dx), dy.shape[0], w.shape[1], w.shape[0], _stream(dev))
+    L.check(rc, "mot_linear_bwd_input")
+
+
+def linear_bwd_weight_out(dy, x, dw_f32, dw_bf16=None) -> None:
+    """dw[Do, K] = dy^T . x reduced in fp32 (split over the tokens), optionally also cast to bf16."""
+    _check_bf16(dy, x, dw_bf16)
+    dev = _require_cuda(dy, x, dw_f32, dw_bf16)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_linear_bwd_weight(_ptr(dy), _ptr(x), _ptr(dw_f32), _ptr(dw_bf16), dy.shape[0], x.shape[1],
+                                           dy.shape[1], _stream(dev))
+    L.check(rc, "mot_linear_bwd_weight")
+
+
+def rmsnorm_forward_out(y, out, eps: float = FP32_EPS) -> None:
+    dev = _require_cuda(y, out)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_rmsnorm_fwd(_ptr(y), _ptr(out), y.shape[0], y.shape[1], _DTYPE[y.dtype], eps, _stream(dev))
+    L.check(rc, "mot_rmsnorm_fwd")
+
+
+def rmsnorm_backward_out(y, grad_out, dy, eps: float = FP32_EPS) -> None:
+    dev = _require_cuda(y, grad_out, dy)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_rmsnorm_bwd(_ptr(y), _ptr(grad_out), _ptr(dy), y.shape[0], y.shape[1], _DTYPE[y.dtype], eps,
+                                     _stream(dev))
+    L.check(rc, "mot_rmsnorm_bwd")
+
+
+class _MotEmbedProjFn(torch.autograd.Function):
+    """out = f_out( [tok | bytes] . W^T + bias ): the fused gather builds the [n, K] operand (mot_embed_fwd, CONCAT),
+    the projection runs on the tensor cores (mot_linear_fwd), the row norm after it is a separate HBM-bound pass over
+    the bf16 product (the reference also rounds F.linear's output to bf16 before its rms_norm).  The [n, K] operand is
+    not kept for the backward: it is gathered again (0.1 ms against 0.7 ms of GEMMs, and n*K*2 bytes less to hold)."""
+
+    @staticmethod
+    def forward(ctx, spec: MixSpec, bpt: int, tokens, byte_ids, E_tok, E_byte, W, bias):
+        dev = _require_cuda(tokens, byte_ids, E_tok, E_byte, W, bias)
+        _check_bf16(E_tok, E_byte)
+        tok = tokens.reshape(-1)
+        tok = (tok if tok.dtype == torch.int32 else tok.to(torch.int32)).contiguous()
+        if byte_ids.dtype not in (torch.int32, torch.int64):
+            raise NotImplementedError("mot_b200: byte ids must be int32 or int64")
+        ids = byte_ids.contiguous()
+        n = tok.numel()
+        if ids.numel() != n * bpt:
+            raise RuntimeError(f"mot_b200: byte ids have {ids.numel()} entries, expected {n}*{bpt}")
+        E_tok_c, E_byte_c = E_tok.contiguous(), E_byte.contiguous()
+        a_spec = dataclasses.replace(spec, combine="concat", out_norm=False)
+        desc = make_desc(a_spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=None, has_lam=False)
+        K, Do = desc.out_dim, W.shape[0]
+        if W.shape[1] != K:
+            raise RuntimeError(f"mot_b200: projection weight is {tuple(W.shape)}, expected [{Do}, {K}]")
+        w16 = W.detach().to(torch.bfloat16).contiguous()      # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
+        ctx.ws, ctx.plan_event = None, None
+        if any(ctx.needs_input_grad[4:6]) and n > 0:
+            ctx.ws = acquire_workspace(desc, dev)
+            ctx.plan_event = embed_plan_async(desc, tok, ctx.ws, dev)
+        A = torch.empty((n, K), dtype=torch.bfloat16, device=dev)
+        embed_forward_out(desc, tok, ids, None, E_tok_c, E_byte_c, None, A)
+        Y = torch.empty((n, Do), dtype=torch.bfloat16, device=dev)
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        linear_forward_out(A, w16, Y, b32)
+        del A
+        if spec.out_norm:
+            out = torch.empty_like(Y)
+            rmsnorm_forward_out(Y, out, spec.eps)
+        else:
+            out = Y
+        ctx.desc, ctx.dev, ctx.spec = desc, dev, spec
+        ctx.w_dtype, ctx.has_bias = W.dtype, bias is not None
+        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tok, ids, E_tok, E_byte, w16, Y = ctx.saved_tensors
+        desc, dev, spec = ctx.desc, ctx.dev, ctx.spec
+        n, K, Do = tok.numel(), desc.out_dim, w16.shape[0]
+        g = grad_out.reshape(n, Do).to(torch.bfloat16).contiguous()
+        if spec.out_norm:
+            dY = torch.empty_like(Y)
+            rmsnorm_backward_out(Y, g, dY, spec.eps)
+        else:
+            dY = g
+        g_bias = dY.float().sum(0) if ctx.has_bias else None
+        A = torch.empty((n, K), dtype=torch.bfloat16, device=dev)
+        embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)       # gathered again, not kept
+        dW32 = torch.empty((Do, K), dtype=torch.float32, device=dev)
+        dW16 = torch.empty((Do, K), dtype=torch.bfloat16, device=dev) if ctx.w_dtype == torch.bfloat16 else None
+        linear_bwd_weight_out(dY, A, dW32, dW16)
+        dA = A                                                                # reuse the buffer
+        linear_bwd_input_out(dY, w16, dA)
+        gE_tok, gE_byte = torch.empty_like(E_tok), torch.empty_like(E_byte)
+        ws, planned = ctx.ws, ctx.plan_event is not None
+        if ws is None:
+            ws = acquire_workspace(desc, dev)
+        if planned:
+            torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+            clean = True
+        else:
+            clean, ws.clean = ws.clean, False
+        embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, dA, gE_tok, gE_byte, None, ws.buf,
+                           plan_ready=planned, ws_clean=clean)
+        ws.clean = True
+        ctx.ws = ctx.plan_event = None
+        release_workspace(ws)
+        gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
+        return None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None)
+
+
+def mot_embed_proj(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Tensor, E_byte: torch.Tensor,
+                   W: torch.Tensor, spec: MixSpec, *, bpt: int = 16, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Concat + dense projection variants: `norm(F.linear(cat([f(tok), f(bytes)]), W))` (runs/7:226-234, runs/72,
+    spt/train_gpt.py:439-443).  spec.tok_norm / byte_norm are the per-input norms, spec.out_norm the norm after the
+    projection, spec.bytes_first the operand order.  Tables bf16; W bf16 (runs) or an fp32 master (spt: cast per call,
+    gradient returned in fp32).  Returns [n_tokens, W.shape[0]] bf16."""
+    return _MotEmbedProjFn.apply(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias)
+
+
 def launch_count() -> int:
     return int(L.lib().mot_launch_count())
 
