@@ -144,6 +144,16 @@ int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
                   void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                   int32_t ws_flags, void* stream);
 
+/* ---- byte pull across tokens ------------------------------------------------------------------------------
+ * Replaces pull_from_left / pull_from_right (spt/data_creation.py:179-305 / :71-176, runs/7:351-428).
+ * bytes_in / bytes_out: [n_rows, tokens_per_row * bpt] int32 or int64 (ids_i64), rows independent; a token whose bpt
+ * bytes all equal eot_byte passes through and resets the pool; from_right == 0: rows are left-padded, every token
+ * receives the last bpt non-pad bytes of its segment up to itself (right-aligned); != 0: the mirror image. */
+size_t mot_pull_workspace_bytes(int64_t n_rows, int64_t tokens_per_row, int32_t bpt);
+int mot_pull(const void* bytes_in, void* bytes_out, int64_t n_rows, int64_t tokens_per_row, int32_t bpt,
+             int32_t ids_i64, int32_t pad_byte, int32_t eot_byte, int32_t from_right, void* workspace,
+             size_t ws_bytes, void* stream);
+
 /* ---- dense projection of the concat+projection variants (tcgen05 tensor cores) -------------------------------
  * bf16 operands, fp32 accumulation in tensor memory.  in_dim = tok_dim + bpt*byte_dim (the row width of the
  * [tok | bytes] operand mot_embed_fwd produces with MOT_CONCAT), out_dim = model_dim; both multiples of 8. */

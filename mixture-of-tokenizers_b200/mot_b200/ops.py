@@ -75,6 +75,37 @@ def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype =
     return out.view(1, -1)
 
 
+def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_byte: int, from_right: bool) -> torch.Tensor:
+    dev = _require_cuda(byte_tensor)
+    if byte_tensor.dtype not in (torch.int32, torch.int64) or byte_tensor.dim() != 2:
+        raise NotImplementedError("mot_b200.pull: byte_tensor must be a 2-D int32 / int64 tensor [B, T*bpt]")
+    B, TB = byte_tensor.shape
+    if TB % bytes_per_token:
+        raise RuntimeError("T must be divisible by bytes_per_token")   # the reference's assert (data_creation.py:189)
+    x = byte_tensor.contiguous()
+    out = torch.empty_like(x)
+    T = TB // bytes_per_token
+    if B * T == 0:
+        return out
+    ws = torch.empty(int(L.lib().mot_pull_workspace_bytes(B, T, bytes_per_token)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().mot_pull(_ptr(x), _ptr(out), B, T, bytes_per_token, 1 if x.dtype == torch.int64 else 0, pad_byte,
+                              eot_byte, 1 if from_right else 0, _ptr(ws), ws.numel(), _stream(dev))
+    L.check(rc, "mot_pull")
+    return out
+
+
+def pull_from_left(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int = 456, eot_byte: int = 457) -> torch.Tensor:
+    """spt/data_creation.py:179-305 (== runs/7:351-428), same signature: every non-EOT token receives the last
+    bytes_per_token non-pad bytes of its segment up to and including itself, right-aligned.  No host syncs."""
+    return _pull(byte_tensor, bytes_per_token, pad_byte, eot_byte, False)
+
+
+def pull_from_right(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int = 456, eot_byte: int = 457) -> torch.Tensor:
+    """spt/data_creation.py:71-176: the first bytes_per_token non-pad bytes of tokens t, t+1, ... before the next EOT."""
+    return _pull(byte_tensor, bytes_per_token, pad_byte, eot_byte, True)
+
+
 def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Optional[torch.Tensor],
               ttb: Optional[torch.Tensor], has_lam: bool, seq_len: int = 0) -> L.MotDesc:
     ref = E_tok if E_tok is not None else E_byte
