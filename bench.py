@@ -264,10 +264,10 @@ def run_ours(args):
     gout = torch.randn(N, Do, generator=gd, device=dev).to(dt)
     lam = torch.tensor([0.5, 0.5], device=dev) if w["variant"] in ("V3c", "V3d") else None
     out = torch.empty(N, Do, dtype=dt, device=dev)
-    # one flat gradient bucket [gE_tok | gE_byte] -> a single NCCL all-reduce
-    n_tok_g, n_byte_g = V_TOK * Dt, V_BYTE * bd
-    flat = torch.empty(n_tok_g + n_byte_g, dtype=dt, device=dev)
-    gE_tok, gE_byte = flat[:n_tok_g].view(V_TOK, Dt), flat[n_tok_g:].view(V_BYTE, bd)
+    # one flat gradient bucket [gE_tok | gE_byte] the backward writes into -> a single NCCL all-reduce
+    from mot_b200 import dp
+    bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False)])
+    gE_tok, gE_byte = bucket.views()
     g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
     ws = ops.acquire_workspace(desc, dev)   # kept across steps: every completed backward leaves it clean (no memset)
@@ -276,14 +276,14 @@ def run_ours(args):
     def step():
         # the same call sequence as mot_b200.mot_embed + autograd: the backward plan (counting sort of the token ids)
         # is launched on a side stream beside the forward kernel, the backward waits for it
-        ev = ops.embed_plan_async(desc, tok, ws, dev)
+        ops.embed_plan_async(desc, tok, ws, dev)
         ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
-        main_stream.wait_event(ev)
+        ops.embed_plan_join(ws, dev)
         ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf,
                                plan_ready=True, ws_clean=True)
         ws.clean = True
         if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            bucket.all_reduce_avg()
 
     def barrier():
         if world > 1:
@@ -340,6 +340,7 @@ def run_ours(args):
         mod = mot_b200.MoTEmbedding(V_TOK, V_BYTE, Dt, bd, bpt, variant=w["variant"]).to(dev).to(dt)
         with torch.no_grad():
             mod.embed_tokens.weight.copy_(E_tok); mod.embed_bytes.weight.copy_(E_byte)
+        mod_bucket = mod.attach_grad_bucket()
         res_host = torch.empty(V_BYTE, bd, dtype=dt).pin_memory()
 
         def e2e_step():
@@ -350,8 +351,7 @@ def run_ours(args):
             x = mod(t_in, b_in)
             x.backward(gout.view_as(x))
             if world > 1:
-                for p_ in mod.parameters():
-                    dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+                mod_bucket.all_reduce_avg()
             res_host.copy_(mod.embed_bytes.weight.grad, non_blocking=True)
             torch.cuda.current_stream().synchronize()   # the caller reads the result on the host every step
 

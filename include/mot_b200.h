@@ -133,6 +133,13 @@ int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
 int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
                    void* stream);
 
+/* The same plan on a second stream, beside the forward: records ev_fork on main_stream, makes side_stream wait for it,
+ * runs the plan there and records ev_join; the stream that later runs mot_embed_bwd (MOT_WS_PLAN_READY) must wait for
+ * ev_join first (mot_stream_wait_event).  Streams are cudaStream_t, events cudaEvent_t, all owned by the caller. */
+int mot_embed_plan_async(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
+                         void* main_stream, void* side_stream, void* ev_fork, void* ev_join);
+int mot_stream_wait_event(void* stream, void* event);
+
 /* Fused backward: the autograd graph of the lines above (rms_norm bwd, split, and the two
  * embedding_dense_backward scatter-adds).  gE_tok [tok_vocab, tok_dim] and gE_byte
  * [byte_vocab, byte_dim] are DENSE and fully overwritten (rows never gathered get zeros), so a

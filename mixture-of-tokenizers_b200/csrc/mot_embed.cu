@@ -266,6 +266,26 @@ extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* worksp
   return run_plan(p, s);
 }
 
+extern "C" int mot_embed_plan_async(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
+                                    void* main_stream, void* side_stream, void* ev_fork, void* ev_join) {
+  if (!side_stream || !ev_fork || !ev_join) return MOT_ERR_BAD_ARG;
+  cudaStream_t ms = reinterpret_cast<cudaStream_t>(main_stream), ss = reinterpret_cast<cudaStream_t>(side_stream);
+  cudaEvent_t ef = reinterpret_cast<cudaEvent_t>(ev_fork), ej = reinterpret_cast<cudaEvent_t>(ev_join);
+  // fork: the plan starts after everything already queued on the main stream (token ids ready, the previous
+  // backward done with the workspace) and runs beside whatever the caller queues next (the forward kernel)
+  if (cudaEventRecord(ef, ms) != cudaSuccess || cudaStreamWaitEvent(ss, ef, 0) != cudaSuccess) return check_launch();
+  if (int rc = mot_embed_plan(d, tok, workspace, ws_bytes, ws_flags, side_stream)) return rc;
+  if (cudaEventRecord(ej, ss) != cudaSuccess) return check_launch();
+  return MOT_OK;
+}
+
+extern "C" int mot_stream_wait_event(void* stream, void* event) {
+  if (!event) return MOT_ERR_BAD_ARG;
+  if (cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaEvent_t>(event), 0) != cudaSuccess)
+    return check_launch();
+  return MOT_OK;
+}
+
 extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                              void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "mot_embed_fwd": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "mot_embed_workspace_init": (C.c_int, [C.POINTER(MotDesc), _P, C.c_size_t, _P]),
     "mot_embed_plan": (C.c_int, [C.POINTER(MotDesc), _P, _P, C.c_size_t, C.c_int32, _P]),
+    "mot_embed_plan_async": (C.c_int, [C.POINTER(MotDesc), _P, _P, C.c_size_t, C.c_int32, _P, _P, _P, _P]),
+    "mot_stream_wait_event": (C.c_int, [_P, _P]),
     "mot_embed_bwd": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                 C.c_int32, _P]),
     "mot_pull_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),

@@ -48,6 +48,16 @@ class MoTEmbedding(nn.Module):
         self.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim) if variant != "V0" else None
         self.lambdas = nn.Parameter(torch.tensor([0.5, 0.5])) if variant in _LAMBDA_VARIANTS else None
         self.register_buffer("ttb", ttb, persistent=False)
+        self.grad_bucket = None
+
+    def attach_grad_bucket(self, bucket=None):
+        """Data parallelism: let the backward kernels write `embed_tokens.weight.grad` / `embed_bytes.weight.grad`
+        straight into one flat bucket, so the per-parameter all-reduces of the reference (runs/7:697-700) become a
+        single `bucket.all_reduce_avg()`.  Call after the module is on its device and in its final dtype."""
+        from .dp import GradBucket
+        tables = [m.weight for m in (self.embed_tokens, self.embed_bytes) if m is not None]
+        self.grad_bucket = bucket if bucket is not None else GradBucket(tables)
+        return self.grad_bucket
 
     def forward(self, token_inputs: torch.Tensor, byte_inputs: Optional[torch.Tensor] = None) -> torch.Tensor:
         assert token_inputs.ndim == 1  # runs/71:300
@@ -62,8 +72,16 @@ class MoTEmbedding(nn.Module):
                       self.embed_tokens.weight if self.embed_tokens is not None else None,
                       self.embed_bytes.weight if self.embed_bytes is not None else None,
                       spec, bpt=self.bpt, lam=lam, ttb=self.ttb if byte_inputs is None else None,
-                      seq_len=token_inputs.numel())
+                      seq_len=token_inputs.numel(), grad_bufs=self._grad_bufs())
         return x[None]
+
+    def _grad_bufs(self):
+        if self.grad_bucket is None:
+            return None
+        b = self.grad_bucket
+        tw = self.embed_tokens.weight if self.embed_tokens is not None else None
+        bw = self.embed_bytes.weight if self.embed_bytes is not None else None
+        return ((tw, b.view_of(tw)) if tw is not None else None, (bw, b.view_of(bw)) if bw is not None else None)
 
 
 # variant name -> MixSpec kwargs of the concat + dense projection family

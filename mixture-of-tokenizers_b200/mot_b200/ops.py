@@ -51,6 +51,26 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the common case costs one integer compare)."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.dev.index is not None and self.dev.index != self.prev:
+            torch.cuda.set_device(self.dev)
+        else:
+            self.prev = -1
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
     """tokens_to_bytes (spt/data_creation.py:61-67): [B,T] -> [B, T*bpt], [T] -> [1, T*bpt].
 
@@ -66,7 +86,7 @@ def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype =
     V, bpt = ttb.shape
     n = tok.numel()
     out = torch.empty((n, bpt), dtype=out_dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_ttb_expand(_ptr(tok), n, _ptr(ttb), V, bpt, _TTB_DTYPE[ttb.dtype], _ptr(out),
                                     1 if out_dtype == torch.int64 else 0, _stream(dev))
     L.check(rc, "mot_ttb_expand")
@@ -88,7 +108,7 @@ def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_by
     if B * T == 0:
         return out
     ws = torch.empty(int(L.lib().mot_pull_workspace_bytes(B, T, bytes_per_token)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_pull(_ptr(x), _ptr(out), B, T, bytes_per_token, 1 if x.dtype == torch.int64 else 0, pad_byte,
                               eot_byte, 1 if from_right else 0, _ptr(ws), ws.numel(), _stream(dev))
     L.check(rc, "mot_pull")
@@ -144,12 +164,12 @@ def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Opt
                      Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps)
 
 
-def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out) -> None:
+def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None) -> None:
     """mot_embed_fwd on caller-allocated tensors (no allocation, no sync; CUDA-graph capturable)."""
     dev = out.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_embed_fwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
-                                   _ptr(out), _stream(dev))
+                                   _ptr(out), _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_fwd")
 
 
@@ -160,39 +180,45 @@ def embed_workspace_bytes(desc: L.MotDesc) -> int:
 def embed_workspace_init(desc: L.MotDesc, ws) -> None:
     """Zero the head of a fresh workspace once; afterwards every completed backward leaves it clean (MOT_WS_CLEAN)."""
     dev = ws.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_embed_workspace_init(desc, _ptr(ws), ws.numel(), _stream(dev))
     L.check(rc, "mot_embed_workspace_init")
 
 
 def embed_plan(desc: L.MotDesc, tok, ws, ws_clean: bool = False) -> None:
     dev = ws.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_embed_plan(desc, _ptr(tok), _ptr(ws), ws.numel(), L.WS_CLEAN if ws_clean else 0, _stream(dev))
     L.check(rc, "mot_embed_plan")
 
 
 def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
-                       plan_ready: bool = False, ws_clean: bool = False) -> None:
+                       plan_ready: bool = False, ws_clean: bool = False, stream: Optional[int] = None) -> None:
     """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten.  `ws_clean`: the caller
     vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward)."""
     dev = grad_out.device
     flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
                                    _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
-                                   flags, _stream(dev))
+                                   flags, _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_bwd")
 
 
 class Workspace:
     """A backward workspace that remembers whether the library left it clean (so the steady-state step needs no
-    memset).  Instances are recycled through a pool per (device, table geometry)."""
+    memset), plus the fork / join events of the plan that runs on the side stream.  Instances are recycled through a
+    pool per (device, table geometry)."""
 
-    def __init__(self, key):
+    def __init__(self, key, dev):
         self.key = key
         self.buf: Optional[torch.Tensor] = None
         self.clean = False
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        cur = torch.cuda.current_stream(dev)
+        self.ev_fork.record(cur)   # materialise the cudaEvent_t handles
+        self.ev_join.record(cur)
+        self.pending = False       # a plan was launched on the side stream and no backward has consumed it yet
 
     def reserve(self, desc: L.MotDesc, dev) -> torch.Tensor:
         need = embed_workspace_bytes(desc)
@@ -200,6 +226,13 @@ class Workspace:
             self.buf = torch.empty(need, dtype=torch.uint8, device=dev)
             self.clean = False
         return self.buf
+
+    def __del__(self):   # dropped with a plan in flight (forward without backward): keep the allocator off the buffer
+        try:
+            if self.pending and self.buf is not None:
+                self.buf.record_stream(side_stream(self.buf.device))
+        except Exception:
+            pass
 
 
 _WS_POOL: dict = {}
@@ -209,8 +242,10 @@ _SIDE_STREAMS: dict = {}
 def acquire_workspace(desc: L.MotDesc, dev) -> Workspace:
     # the zeroed head of the workspace is laid out by (tok_vocab, byte_vocab, byte_dim): one pool per geometry
     key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine)
-    free = _WS_POOL.setdefault(key, [])
-    ws = free.pop() if free else Workspace(key)
+    free = _WS_POOL.get(key)
+    if free is None:
+        free = _WS_POOL[key] = []
+    ws = free.pop() if free else Workspace(key, dev)
     ws.reserve(desc, dev)
     return ws
 
@@ -229,24 +264,30 @@ def side_stream(dev) -> torch.cuda.Stream:
     return st
 
 
-def embed_plan_async(desc: L.MotDesc, tok, ws: Workspace, dev) -> torch.cuda.Event:
-    """Launch the plan on the side stream, ordered after the work already queued on the current stream; returns the
-    event the backward has to wait for."""
-    cur = torch.cuda.current_stream(dev)
-    side = side_stream(dev)
-    side.wait_stream(cur)
+def embed_plan_async(desc: L.MotDesc, tok, ws: Workspace, dev, stream: Optional[int] = None) -> None:
+    """mot_embed_plan_async: fork from the current stream, run the plan on the side stream, record ws.ev_join.  The
+    backward waits for it with embed_plan_join()."""
     clean, ws.clean = ws.clean, False
-    with torch.cuda.stream(side):
-        embed_plan(desc, tok, ws.buf, ws_clean=clean)
-        ev = side.record_event()
-    ws.buf.record_stream(side)
-    return ev
+    with _on_device(dev):
+        rc = L.lib().mot_embed_plan_async(desc, _ptr(tok), _ptr(ws.buf), ws.buf.numel(), L.WS_CLEAN if clean else 0,
+                                          _stream(dev) if stream is None else stream, side_stream(dev).cuda_stream,
+                                          ws.ev_fork.cuda_event, ws.ev_join.cuda_event)
+    L.check(rc, "mot_embed_plan_async")
+    ws.pending = True
+
+
+def embed_plan_join(ws: Workspace, dev, stream: Optional[int] = None) -> None:
+    rc = L.lib().mot_stream_wait_event(_stream(dev) if stream is None else stream, ws.ev_join.cuda_event)
+    L.check(rc, "mot_stream_wait_event")
+    ws.pending = False
 
 
 class _MotEmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec: MixSpec, bpt: int, seq_len: int, tokens, byte_ids, ttb, E_tok, E_byte, lam):
+    def forward(ctx, spec: MixSpec, bpt: int, seq_len: int, tokens, byte_ids, ttb, E_tok, E_byte, lam, grad_bufs=None):
         dev = _require_cuda(tokens, byte_ids, ttb, E_tok, E_byte, lam)
+        # optional ((param_tok, view_tok), (param_byte, view_byte)): views of a dp.GradBucket that become param.grad
+        ctx.grad_bufs = grad_bufs
         tok = None
         if tokens is not None:
             tok = tokens.reshape(-1)
@@ -269,12 +310,13 @@ class _MotEmbedFn(torch.autograd.Function):
         ref = E_tok_c if E_tok_c is not None else E_byte_c
         out = torch.empty((n, desc.out_dim), dtype=ref.dtype, device=dev)
         # the backward needs the positions grouped by token id: start that sort now, beside the forward kernel
-        ctx.ws, ctx.plan_event = None, None
+        ctx.ws = None
+        st = _stream(dev)
         needs_grad = any(ctx.needs_input_grad[6:9])   # E_tok, E_byte, lam
         if needs_grad and tok is not None and n > 0:
             ctx.ws = acquire_workspace(desc, dev)
-            ctx.plan_event = embed_plan_async(desc, tok, ctx.ws, dev)
-        embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out)
+            embed_plan_async(desc, tok, ctx.ws, dev, st)
+        embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st)
         ctx.desc, ctx.dev = desc, dev
         ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)])
         ctx.present = [t is not None for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)]
@@ -289,36 +331,51 @@ class _MotEmbedFn(torch.autograd.Function):
         g = grad_out.contiguous()
         if g.dtype != (E_tok if E_tok is not None else E_byte).dtype:
             g = g.to((E_tok if E_tok is not None else E_byte).dtype)
-        gE_tok = torch.empty_like(E_tok) if E_tok is not None else None
-        gE_byte = torch.empty_like(E_byte) if E_byte is not None else None
+        direct = [None, None]
+        if ctx.grad_bufs is not None:
+            # the kernels overwrite every row, so they can write straight into the caller's flat bucket; the view is
+            # installed as param.grad here (autograd would clone a view).  With a gradient already accumulated on the
+            # parameter the normal path is taken and autograd adds to it.
+            for i, (pv, E) in enumerate(zip(ctx.grad_bufs, (E_tok, E_byte))):
+                if pv is not None and E is not None and pv[0].grad is None:
+                    direct[i] = pv
+        gE_tok = direct[0][1] if direct[0] is not None else (torch.empty_like(E_tok) if E_tok is not None else None)
+        gE_byte = direct[1][1] if direct[1] is not None else (torch.empty_like(E_byte) if E_byte is not None else None)
         g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
-        ws, planned = ctx.ws, ctx.plan_event is not None
+        st = _stream(dev)
+        ws, planned = ctx.ws, ctx.ws is not None
         if ws is None:
             ws = acquire_workspace(desc, dev)
         if planned:
-            torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+            embed_plan_join(ws, dev, st)
             clean = True          # the plan ran on a clean (or freshly cleared) workspace and leaves it clean
         else:
             clean, ws.clean = ws.clean, False
         embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
-                           plan_ready=planned, ws_clean=clean)
+                           plan_ready=planned, ws_clean=clean, stream=st)
         ws.clean = True           # every completed backward leaves the head of the workspace zeroed
-        ctx.ws = ctx.plan_event = None
+        ctx.ws = None
         release_workspace(ws)
         if g_lam is not None:
             g_lam = g_lam.to(ctx.lam_dtype)
-        return None, None, None, None, None, None, gE_tok, gE_byte, g_lam
+        if direct[0] is not None:
+            direct[0][0].grad, gE_tok = gE_tok, None
+        if direct[1] is not None:
+            direct[1][0].grad, gE_byte = gE_byte, None
+        return None, None, None, None, None, None, gE_tok, gE_byte, g_lam, None
 
 
 def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], E_tok: Optional[torch.Tensor],
               E_byte: Optional[torch.Tensor], spec: MixSpec, *, bpt: int = 16, lam: Optional[torch.Tensor] = None,
-              ttb: Optional[torch.Tensor] = None, seq_len: int = 0) -> torch.Tensor:
+              ttb: Optional[torch.Tensor] = None, seq_len: int = 0, grad_bufs=None) -> torch.Tensor:
     """Fused gather + pool + combine + norm.  Returns [n_tokens, out_dim] in the table dtype.
 
     tokens   int32/int64 [..] (flattened); byte_ids int32/int64 with n_tokens*bpt entries, token-major
     ([.., T*bpt]) or slot-major ([bpt, T], spec.slot_major); byte_ids=None derives the ids from `ttb`
-    inside the kernel.  lam = float tensor [2] = (lam_tok, lam_byte) or None."""
-    return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam)
+    inside the kernel.  lam = float tensor [2] = (lam_tok, lam_byte) or None.  grad_bufs = optional
+    ((param, view), (param, view)) pairs for the token / byte table: the backward writes the dense gradient into `view`
+    (a slice of a dp.GradBucket) and installs it as `param.grad`."""
+    return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam, grad_bufs)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -336,7 +393,7 @@ def linear_forward_out(x, w, y, bias=None) -> None:
     _check_bf16(x, w)
     dev = _require_cuda(x, w, y, bias)
     n, K = x.shape
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, K, w.shape[0],
                                     1 if y.dtype == torch.float32 else 0, _stream(dev))
     L.check(rc, "mot_linear_fwd")
@@ -346,7 +403,7 @@ def linear_bwd_input_out(dy, w, dx) -> None:
     """dx[n, K] = dy[n, Do] . w[Do, K]: mot_linear_bwd_input (w read in place as an MN-major operand)."""
     _check_bf16(dy, w, dx)
     dev = _require_cuda(dy, w, dx)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_linear_bwd_input(_ptr(dy), _ptr(w), _ptr(dx), dy.shape[0], w.shape[1], w.shape[0], _stream(dev))
     L.check(rc, "mot_linear_bwd_input")
 
@@ -355,7 +412,7 @@ def linear_bwd_weight_out(dy, x, dw_f32, dw_bf16=None) -> None:
     """dw[Do, K] = dy^T . x reduced in fp32 (split over the tokens), optionally also cast to bf16."""
     _check_bf16(dy, x, dw_bf16)
     dev = _require_cuda(dy, x, dw_f32, dw_bf16)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_linear_bwd_weight(_ptr(dy), _ptr(x), _ptr(dw_f32), _ptr(dw_bf16), dy.shape[0], x.shape[1],
                                            dy.shape[1], _stream(dev))
     L.check(rc, "mot_linear_bwd_weight")
@@ -363,14 +420,14 @@ def linear_bwd_weight_out(dy, x, dw_f32, dw_bf16=None) -> None:
 
 def rmsnorm_forward_out(y, out, eps: float = FP32_EPS) -> None:
     dev = _require_cuda(y, out)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_rmsnorm_fwd(_ptr(y), _ptr(out), y.shape[0], y.shape[1], _DTYPE[y.dtype], eps, _stream(dev))
     L.check(rc, "mot_rmsnorm_fwd")
 
 
 def rmsnorm_backward_out(y, grad_out, dy, eps: float = FP32_EPS) -> None:
     dev = _require_cuda(y, grad_out, dy)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = L.lib().mot_rmsnorm_bwd(_ptr(y), _ptr(grad_out), _ptr(dy), y.shape[0], y.shape[1], _DTYPE[y.dtype], eps,
                                      _stream(dev))
     L.check(rc, "mot_rmsnorm_bwd")
@@ -401,10 +458,10 @@ class _MotEmbedProjFn(torch.autograd.Function):
         if W.shape[1] != K:
             raise RuntimeError(f"mot_b200: projection weight is {tuple(W.shape)}, expected [{Do}, {K}]")
         w16 = W.detach().to(torch.bfloat16).contiguous()      # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
-        ctx.ws, ctx.plan_event = None, None
+        ctx.ws = None
         if any(ctx.needs_input_grad[4:6]) and n > 0:
             ctx.ws = acquire_workspace(desc, dev)
-            ctx.plan_event = embed_plan_async(desc, tok, ctx.ws, dev)
+            embed_plan_async(desc, tok, ctx.ws, dev)
         A = torch.empty((n, K), dtype=torch.bfloat16, device=dev)
         embed_forward_out(desc, tok, ids, None, E_tok_c, E_byte_c, None, A)
         Y = torch.empty((n, Do), dtype=torch.bfloat16, device=dev)
@@ -441,18 +498,18 @@ class _MotEmbedProjFn(torch.autograd.Function):
         dA = A                                                                # reuse the buffer
         linear_bwd_input_out(dY, w16, dA)
         gE_tok, gE_byte = torch.empty_like(E_tok), torch.empty_like(E_byte)
-        ws, planned = ctx.ws, ctx.plan_event is not None
+        ws, planned = ctx.ws, ctx.ws is not None
         if ws is None:
             ws = acquire_workspace(desc, dev)
         if planned:
-            torch.cuda.current_stream(dev).wait_event(ctx.plan_event)
+            embed_plan_join(ws, dev)
             clean = True
         else:
             clean, ws.clean = ws.clean, False
         embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, dA, gE_tok, gE_byte, None, ws.buf,
                            plan_ready=planned, ws_clean=clean)
         ws.clean = True
-        ctx.ws = ctx.plan_event = None
+        ctx.ws = None
         release_workspace(ws)
         gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
         return None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None)

@@ -266,3 +266,27 @@ def test_unsupported_and_bad_arguments():
     Et128 = torch.randn(10, 128, device=d).bfloat16().requires_grad_(True)
     out = mot_b200.mot_embed(toks[:0], ids[:0], Et128, Eb8, mot_b200.MixSpec(combine="add"), bpt=16)
     assert tuple(out.shape) == (0, 128)
+
+
+def test_module_backward_writes_into_grad_bucket():
+    """Data-parallel path: with a GradBucket attached the backward kernels write the dense gradients straight into
+    the flat bucket (param.grad is a view of it) and the values equal the un-bucketed run."""
+    import mot_b200
+    d = dev()
+    torch.manual_seed(3)
+    m = mot_b200.MoTEmbedding(1000, 458, 256, 16, 16, variant="V3").to(d).bfloat16()
+    toks = torch.randint(0, 1000, (300,), device=d, dtype=torch.int32)
+    ids = torch.randint(0, 458, (16, 300), device=d, dtype=torch.int32)
+    gout = torch.randn(1, 300, 256, device=d).bfloat16()
+    m(toks, ids).backward(gout)
+    want_tok, want_byte = m.embed_tokens.weight.grad.clone(), m.embed_bytes.weight.grad.clone()
+    for p in m.parameters():
+        p.grad = None
+    bucket = m.attach_grad_bucket()
+    m(toks, ids).backward(gout)
+    assert m.embed_tokens.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    assert m.embed_bytes.weight.grad.data_ptr() == bucket.view_of(m.embed_bytes.weight).data_ptr()
+    # fp32 summation order of duplicates / atomics differs run to run: same bar as against the oracle
+    assert nerr(m.embed_tokens.weight.grad, want_tok) <= 2.0 ** -8
+    assert nerr(m.embed_bytes.weight.grad, want_byte) <= 2.0 ** -8
+    assert bucket.all_reduce_avg() is None   # single process: no collective

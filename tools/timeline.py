@@ -30,9 +30,9 @@ desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam
 ws = ops.acquire_workspace(desc, d)
 main_stream = torch.cuda.current_stream(d)
 def step():
-    ev = ops.embed_plan_async(desc, tok, ws, d)
+    ops.embed_plan_async(desc, tok, ws, d)
     ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
-    main_stream.wait_event(ev)
+    ops.embed_plan_join(ws, d)
     ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf, plan_ready=True, ws_clean=True)
     ws.clean = True
 for _ in range(10):
