@@ -159,7 +159,7 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
 }
 
 struct WsLayout {
-  size_t cnt, byte_acc, lam_acc, zero_end, off, order, stok, partial, total;
+  size_t cnt, byte_acc, lam_acc, partial, zero_end, off, order, stok, total;
 };
 
 static WsLayout ws_layout(const EmbedParams& p) {
@@ -172,15 +172,15 @@ static WsLayout ws_layout(const EmbedParams& p) {
     o = align_up(o + bytes, 256);
     return at;
   };
-  // zeroed region first: cnt | byte_acc | lam_acc (one memset)
+  // zeroed region first: cnt | byte_acc | lam_acc | partial (one memset, only when the caller does not pass MOT_WS_CLEAN)
   w.cnt = take((size_t)V * 4);
   w.byte_acc = take((size_t)p.n_rep * (p.Vb > 0 ? p.Vb : 1) * p.bd * 4);
   w.lam_acc = take(16);
+  w.partial = take((size_t)n_stream_chunks * (p.Dt > 0 ? p.Dt : 8) * 4);
   w.zero_end = o;
   w.off = take((size_t)(V + 1) * 4);
   w.order = take((size_t)N * 4);
   w.stok = take((size_t)N * 4);
-  w.partial = take((size_t)2 * n_stream_chunks * (p.Dt > 0 ? p.Dt : 8) * 4);
   w.total = o;
   return w;
 }

@@ -51,7 +51,7 @@ struct EmbedParams {
   int* off;         // [V+1]   exclusive scan of cnt
   int* order;       // [N]     positions grouped by token id (the token-sorted stream)
   int* stok;        // [N]     token id of every stream entry
-  float* partial;   // [2*n_stream_chunks, Dt] fp32 partial row sums (rows that straddle a chunk boundary)
+  float* partial;   // [n_stream_chunks, Dt] fp32 slots, zero on entry: sums of the rows that straddle chunk boundaries
   float* byte_acc;  // [n_rep, Vb*bd] fp32, zeroed per call
   float* lam_acc;   // [2]
   long long N, T;
@@ -657,18 +657,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   bool seg_lead = false;  // current row segment started at the chunk start and continues a row of the previous chunk
   float tscale = lam_t;   // lam_t * r_t of the current row
 
-  // flush the current row segment: direct write if the whole row lies inside this chunk, else fp32 partial
-  auto flush = [&](int chunk, bool trail) {
+  // flush the current row segment: direct write if the whole row lies inside this chunk, else fp32 RED into its slot
+  auto flush = [&](bool trail) {
     const T* trow = reinterpret_cast<const T*>(ring + (size_t)ps * L.stage_bytes + L.g_bytes);
     if (!seg_lead && !trail) {
       const float d = finish_tok_row<T, CPL, MODE>(p, cm, cur_v, Du, trow, lam_t);
       if (lane == 0) dlam_t += d;
     } else {
-      float* prow = p.partial + (size_t)(2 * chunk + (seg_lead ? 0 : 1)) * p.Dt;
+      // the row continues in another chunk: add this segment into the fp32 slot of the row's FIRST chunk (a chunk is
+      // the first chunk of at most one such row: its last one).  Hot rows spread over many chunks meet there through
+      // the L2 atomic units; the finalize kernel reads the one slot, writes the row and zeroes the slot again.
+      const int c_first = __ldg(p.off + cur_v) / p.R;
+      float* prow = p.partial + (size_t)c_first * p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (MOT_TOK_OK(it))
-          *reinterpret_cast<float4*>(prow + MOT_TOFF(it)) = make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]);
+          atomicAdd(reinterpret_cast<float4*>(prow + MOT_TOFF(it)), make_float4(Du[it][0], Du[it][1], Du[it][2], Du[it][3]));
       }
     }
 #pragma unroll
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       const int v = __shfl_sync(0xffffffffu, A.v, k);
       const bool new_row = has_tok && v != cur_v;
       if (new_row) {  // flush BEFORE refilling the ring: the old row's token row sits in stage (consumed-1) % D
-        if (cur_v >= 0) flush(chunk, false);
+        if (cur_v >= 0) flush(false);
         seg_lead = chunk_first && k == 0 && v == v_before;
         cur_v = v;
       }
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
     if (chunk_last && has_tok && cur_v >= 0) {
       const int b_end = chunk * p.R + p.R;
       const bool trail = b_end < Ni && __ldg(p.stok + b_end) == cur_v;
-      flush(chunk, trail);
+      flush(trail);
       cur_v = -1;
       seg_lead = false;
     }
@@ -894,9 +898,8 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
       const long long bnd = (c0 + 1) * (long long)p.R;  // first stream entry of chunk c0 + 1
       const int v = __ldg(p.stok + bnd - 1);
       if (__ldg(p.stok + bnd) != v) continue;                  // no row crosses this boundary
-      const int o0 = __ldg(p.off + v), o1 = __ldg(p.off + v + 1);
-      if (o0 < c0 * (long long)p.R) continue;                  // the row started in an earlier chunk: not ours
-      const long long c1 = (o1 - 1) / p.R;                     // last chunk of the row
+      if (__ldg(p.off + v) < c0 * (long long)p.R) continue;    // the row started in an earlier chunk: not ours
+      float* prow = p.partial + (size_t)c0 * p.Dt;             // all segments of the row were added here
       const T* trow = E_tok + (size_t)v * p.Dt;
       float dot = 0.f, ss = 0.f;
       // pass 0 (only when the token-norm backward or d lam_tok need <Du, t> and |t|^2), pass 1 writes the row
@@ -908,16 +911,9 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
         for (int c = lane; c < p.Dt / kChunk; c += 32) {
           float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, du[8];
           if (tok_norm || has_lam) Vec8<T>::unpack(Vec8<T>::ldg_raw(trow + c * kChunk), tv);
-          {
-            const float* pr = p.partial + (size_t)(2 * c0 + 1) * p.Dt + c * kChunk;  // trailing partial of c0
-            const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
-            du[0] = x.x; du[1] = x.y; du[2] = x.z; du[3] = x.w; du[4] = y.x; du[5] = y.y; du[6] = y.z; du[7] = y.w;
-          }
-          for (long long cc = c0 + 1; cc <= c1; ++cc) {                                // leading partials
-            const float* pr = p.partial + (size_t)(2 * cc) * p.Dt + c * kChunk;
-            const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
-            du[0] += x.x; du[1] += x.y; du[2] += x.z; du[3] += x.w; du[4] += y.x; du[5] += y.y; du[6] += y.z; du[7] += y.w;
-          }
+          float* pr = prow + c * kChunk;
+          const float4 x = *reinterpret_cast<const float4*>(pr), y = *reinterpret_cast<const float4*>(pr + 4);
+          du[0] = x.x; du[1] = x.y; du[2] = x.z; du[3] = x.w; du[4] = y.x; du[5] = y.y; du[6] = y.z; du[7] = y.w;
           if (pass == 0) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -929,6 +925,9 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = a_ * du[e] - b_ * tv[e];
             Vec8<T>::stg(G + (size_t)v * p.Dt + c * kChunk, o);
+            // leave the slot zeroed for the next call (self-cleaning workspace, MOT_WS_CLEAN)
+            *reinterpret_cast<float4*>(pr) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(pr + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if (pass == 0) {
