@@ -593,9 +593,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       iw = 1;
       ik = 0;
     }
-    const int pos = __shfl_sync(0xffffffffu, iw ? B.pos : A.pos, ik);
-    const int v = __shfl_sync(0xffffffffu, iw ? B.v : A.v, ik);
-    if (lane == 0) {
+    if (lane == ik) {  // the lane that holds entry ik of the batch issues its two row copies (no broadcast needed)
+      const int pos = iw ? B.pos : A.pos, v = iw ? B.v : A.v;
       unsigned char* st = ring + (size_t)is * L.stage_bytes;
       mbar_expect_tx(bars + is, g_bytes + t_bytes);
       bulk_g2s(st, gout + (size_t)pos * p.Do, g_bytes, bars + is);
@@ -697,8 +696,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         seg_lead = chunk_first && k == 0 && v == v_before;
         cur_v = v;
       }
-      while (issued - consumed < D && try_issue()) {
-      }
+      if (issued - consumed < D) try_issue();  // one stage was freed by the previous occurrence
       const int idreg = clamp_id(p, id_next);
       const int pos_ahead = __shfl_sync(0xffffffffu, A.pos, (k + 1) & 31);
       if (id_lane && k + 1 < A.cnt) id_next = load_raw_id(p, idsrc, pos_ahead, lane);
@@ -732,7 +730,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) idv[it] = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
       // z = tscale * t + lam_b * rs * b
-      float z[CPL][CW];
+      float z[CPL][CW], gr[CPL][CW];  // mixed row and upstream gradient row of this occurrence
       float ss = 0.f, gz = 0.f;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
@@ -774,16 +772,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
             }
           }
         }
-        if (out_norm) {
-          if (MOT_CHUNK_OK(it)) {
-            float g[CW];
-            V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), g);
+        if (MOT_CHUNK_OK(it)) {
+          V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), gr[it]);
+          if (out_norm) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) {
               ss += z[it][e] * z[it][e];
-              gz += g[e] * z[it][e];
+              gz += gr[it][e] * z[it][e];
             }
           }
+        } else {
+#pragma unroll
+          for (int e = 0; e < CW; ++e) gr[it][e] = 0.f;
         }
       }
       float r_o = 1.f, coef = 0.f;
@@ -797,11 +797,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         const bool valid = MOT_CHUNK_OK(it);  // lane-dependent: no warp collectives under it
         float dz[CW];
         if (valid) {
-          V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), dz);
-          if (out_norm) {
 #pragma unroll
-            for (int e = 0; e < CW; ++e) dz[e] = r_o * dz[e] - coef * z[it][e];
-          }
+          for (int e = 0; e < CW; ++e) dz[e] = out_norm ? r_o * gr[it][e] - coef * z[it][e] : gr[it][e];
           if (MOT_TOK_OK(it)) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) Du[it][e] += dz[e];
@@ -859,6 +856,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
     A = B;
     if (iw == 1) iw = 0; else ik = 0;
     load_next(B);
+    while (issued - consumed < D && try_issue()) {  // the issue cursor may have been waiting for this batch
+    }
   }
 
   // ---- lambda partials ----
