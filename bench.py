@@ -46,6 +46,10 @@ WORKLOADS = {
     "mot-sum-1m": dict(variant="V3", N=1048576, Dt=1024, bd=64, bpt=16, dtype="bf16"),
     "mot-concat-711": dict(variant="V4", N=65536, Dt=512, bd=32, bpt=16, dtype="bf16"),
     "mot-norm-lambdas-71041": dict(variant="V3d", N=65536, Dt=1024, bd=64, bpt=16, dtype="bf16"),
+    # concat + dense projection (tensor-core bound): runs/7 (1024/64 -> 1024, K = 2048, runs/7:496-503) and the
+    # scaled-pre-train default (256/48 -> 1024, K = 1024, B=64 x S=1024 per GPU, spt/train_gpt.py:822)
+    "mot-proj-runs7-64k": dict(variant="V1", N=65536, Dt=1024, bd=64, bpt=16, Do=1024, dtype="bf16"),
+    "mot-proj-spt-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16"),
 }
 DEFAULT_WORKLOAD = "mot-sum-124M-48k"
 
@@ -77,7 +81,7 @@ def algorithmic_bytes(w):
     """BASELINE.md section 3 (ids given as a tensor, R = 1 because the mixed row is normalised)."""
     e = 2 if w["dtype"] == "bf16" else 4
     N, Dt, bd, bpt = w["N"], w["Dt"], w["bd"], w["bpt"]
-    Do = {"V3": Dt, "V3d": Dt, "V4": Dt + bpt * bd}[w["variant"]]
+    Do = {"V3": Dt, "V3d": Dt, "V4": Dt + bpt * bd, "V1": w.get("Do", Dt)}[w["variant"]]
     fwd = N * (4 + 4 * bpt + Dt * e + Do * e) + V_BYTE * bd * e
     bwd = N * (Do * e + 4 + 4 * bpt + Dt * e) + V_TOK * Dt * e + V_BYTE * bd * e
     return fwd, bwd, Do
@@ -153,6 +157,14 @@ def measured_traffic(workload, kernel):
         return None
 
 
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,11 +188,15 @@ def cpu_reference_step_fn(w, n_sample, seed=12345):
     dt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
     toks = torch.randint(0, V_TOK - 1, (n_sample,), generator=g, dtype=torch.int32)
     slot_major = w["variant"].startswith("V3")
+    Do = w.get("Do", Do)
     ids = torch.randint(0, V_BYTE, (bpt, n_sample) if slot_major else (1, n_sample * bpt), generator=g, dtype=torch.int32)
     E_tok = torch.randn(V_TOK, Dt, generator=g).to(dt)   # nn.Embedding N(0,1) -> bf16 (train_gpt.py:1124-1126)
     E_byte = torch.randn(V_BYTE, bd, generator=g).to(dt)
     gout = torch.randn(n_sample, Do, generator=g).to(dt)
     kw = dict(bpt=bpt, slot_major=slot_major)
+    if w["variant"] == "V1":
+        K = Dt + bpt * bd
+        kw["W"] = ((torch.rand(w["Do"], K, generator=g) * 2 - 1) * (3 ** 0.5) * 0.5 * K ** -0.5).to(dt)
     if w["variant"] in ("V3c", "V3d"):
         kw["lam_tok"], kw["lam_byte"] = torch.tensor(0.5), torch.tensor(0.5)
 
@@ -407,9 +423,173 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# GPU arm, concat + dense projection workloads (tensor-core bound)
+# ----------------------------------------------------------------------------------------------
+def run_proj(args):
+    import torch.distributed as dist
+    import mot_b200
+    from mot_b200 import ops, dp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    w = workload_config(args)
+    N, Dt, bd, bpt, Do = w["N"], w["Dt"], w["bd"], w["bpt"], w["Do"]
+    K = Dt + bpt * bd
+    dt = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(12345)
+    E_tok = torch.randn(V_TOK, Dt, generator=g, device=dev).to(dt)
+    E_byte = torch.randn(V_BYTE, bd, generator=g, device=dev).to(dt)
+    W = ((torch.rand(Do, K, generator=g, device=dev) * 2 - 1) * (3 ** 0.5) * 0.5 * K ** -0.5).to(dt)
+    gd = torch.Generator(device=dev).manual_seed(12345 + 1000 * (rank + 1))
+    tok_host = make_tokens(N, args.dist, 12345 + rank).pin_memory()
+    tok = tok_host.to(dev)
+    ids = torch.randint(0, V_BYTE, (1, N * bpt), generator=gd, device=dev, dtype=torch.int32)
+    ids_host = ids.cpu().pin_memory()
+    gout = torch.randn(N, Do, generator=gd, device=dev).to(dt)
+    spec = mot_b200.MixSpec(combine="concat", tok_norm=True, byte_norm=True, out_norm=False)   # the [tok | bytes] operand
+    desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=False)
+    ws = ops.acquire_workspace(desc, dev)
+    A = torch.empty(N, K, dtype=dt, device=dev)
+    Y, out, dY = (torch.empty(N, Do, dtype=dt, device=dev) for _ in range(3))
+    dW32 = torch.empty(Do, K, dtype=torch.float32, device=dev)
+    bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False),
+                            torch.nn.Parameter(W, requires_grad=False)])
+    gE_tok, gE_byte, gW = bucket.views()
+    ev = {k: [] for k in ("fwd", "dx", "dw")}
+
+    def timed(key, fn, record):
+        if not record:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        ev[key].append((a, b))
+
+    def step(record=False):
+        # forward: fused gather of [tok | bytes] -> tcgen05 projection -> rms_norm   (runs/7:317-319,233-234)
+        ops.embed_plan_async(desc, tok, ws, dev)
+        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)
+        timed("fwd", lambda: ops.linear_forward_out(A, W, Y), record)
+        ops.rmsnorm_forward_out(Y, out)
+        # backward: norm bwd -> dW, dX on the tensor cores -> fused scatter into the dense table gradients
+        ops.rmsnorm_backward_out(Y, gout, dY)
+        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)      # operand gathered again, not kept
+        timed("dw", lambda: ops.linear_bwd_weight_out(dY, A, dW32, gW), record)
+        timed("dx", lambda: ops.linear_bwd_input_out(dY, W, A), record)          # dX overwrites the operand buffer
+        ops.embed_plan_join(ws, dev)
+        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, A, gE_tok, gE_byte, None, ws.buf,
+                               plan_ready=True, ws_clean=True)
+        ws.clean = True
+        if world > 1:
+            bucket.all_reduce_avg()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    K_steps = args.steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
+    mot_b200.reset_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K_steps):
+        step()
+    e1.record()
+    barrier()
+    launches = mot_b200.launch_count()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K_steps
+    value = world * N / (ms_step * 1e-3)
+    for _ in range(K_steps):       # instrumented pass: events around the three GEMM calls
+        step(record=True)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in ev.items()}
+
+    e2e = None
+    if not args.no_e2e:
+        mod = mot_b200.MoTProjEmbedding(V_TOK, V_BYTE, Dt, bd, Do, bpt, variant="V1").to(dev).to(dt)
+        res_host = torch.empty(V_BYTE, bd, dtype=dt).pin_memory()
+
+        def e2e_step():
+            for p_ in mod.parameters():
+                p_.grad = None
+            x = mod(tok_host.to(dev, non_blocking=True), ids_host.to(dev, non_blocking=True))
+            x.backward(gout.view_as(x))
+            if world > 1:
+                for p_ in mod.parameters():
+                    dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+            res_host.copy_(mod.embed_bytes.weight.grad, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        Ke = max(10, K_steps // 4)
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        barrier()
+        t_e = torch.tensor([(time.perf_counter() - t0) / Ke], device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N / float(t_e.item()), "unit": "tokens/s",
+               "h2d_bytes_per_step": tok_host.numel() * 4 + ids_host.numel() * 4, "d2h_bytes_per_step": res_host.numel() * 2,
+               "ms_per_step": float(t_e.item()) * 1e3, "api": "mot_b200.MoTProjEmbedding.forward + autograd backward", "steps": Ke}
+
+    if rank == 0:
+        peak, peak_src = measured_tensor_peak()
+        flops = 2.0 * N * K * Do
+        tot_ms = sum(gemm_ms.values())
+        achieved = 3 * flops / (tot_ms * 1e-3) / 1e12
+        line = {
+            "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": K_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], "variant": "V1 concat+projection (runs/7:226-234,317-319)",
+                       "tokens_per_gpu_per_step": N, "token_dim": Dt, "byte_dim": bd, "bytes_per_token": bpt, "in_dim": K,
+                       "out_dim": Do, "token_dist": args.dist, "l2": "working set > 126 MB L2, no flush",
+                       "parallelism": f"dp{world}" + (", one flat-bucket NCCL all-reduce(AVG) per step" if world > 1 else "")},
+            "tokens_per_sec_per_gpu": value / world,
+            "kernel_ms": {"linear_fwd": gemm_ms["fwd"], "linear_bwd_input": gemm_ms["dx"], "linear_bwd_weight": gemm_ms["dw"]},
+            "roofline": {"bound": "tensor", "kernel": "mot_gemm_kernel (fwd + dX + dW)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "flops_per_launch": flops,
+                         "peak_source": peak_src,
+                         "per_kernel_tflops": {k: flops / (v * 1e-3) / 1e12 for k, v in gemm_ms.items()},
+                         "timing": "CUDA event pairs around each projection call in a second pass of the same K steps"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_cpu_reference(w, steps=20, warmup=1, budget_s=15.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif WORKLOADS[a.workload]["variant"] == "V1":
+        run_proj(a)
     else:
         run_ours(a)

@@ -144,6 +144,8 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.flags = d->flags;
   p.ttb_dtype = d->ttb_dtype;
   p.n_chunks = d->out_dim / kChunk;
+  p.io_ld = d->out_dim;
+  p.io_col = 0;
   p.eps = d->eps;
   // stream chunk size: one chunk per backward warp of a full B200 (148 SMs x kBwdThreads/32 warps), so that every
   // warp walks the same number of stream entries; chunks longer than one 32-entry batch are whole batches.
@@ -156,6 +158,30 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.n_rep = kByteRep;
   p.stages = 4;
   p.tab_smem = 1;
+}
+
+// A concat without a norm over the concatenated row and without lambdas (the [tok | bytes] operand of the projection
+// variants, runs/7:226-232) is two independent halves: columns [0, Dt) depend on the token only, the rest on the byte
+// ids only.  They run as a tok-only and a bytes-only launch over the strided rows: half the row per lane (no register
+// spills at 2048-wide rows), and the bytes half needs neither the token rows nor the sorted stream.
+static bool concat_splits(const MotDesc* d) {
+  return d->combine == MOT_CONCAT && !(d->flags & (MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS));
+}
+static void split_params(const MotDesc* d, EmbedParams& pt, EmbedParams& pb) {
+  const int db = d->bpt * d->byte_dim;
+  const bool bytes_first = (d->flags & MOT_F_BYTES_FIRST) != 0;
+  MotDesc dt = *d, dbd = *d;
+  dt.combine = MOT_TOK_ONLY;
+  dt.out_dim = d->tok_dim;
+  dt.flags = d->flags & MOT_F_TOK_NORM;
+  dbd.combine = MOT_BYTES_ONLY;
+  dbd.out_dim = db;
+  dbd.flags = d->flags & ~(MOT_F_TOK_NORM | MOT_F_BYTES_FIRST);
+  fill_params(&dt, pt);
+  fill_params(&dbd, pb);
+  pt.io_ld = pb.io_ld = d->out_dim;
+  pt.io_col = bytes_first ? db : 0;
+  pb.io_col = bytes_first ? 0 : d->tok_dim;
 }
 
 struct WsLayout {
@@ -230,10 +256,19 @@ extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* b
   }
   if ((d->flags & MOT_F_HAS_LAMBDAS) && !lam) return MOT_ERR_BAD_ARG;
   if (!aligned16(out) || !aligned16(E_tok) || !aligned16(E_byte)) return MOT_ERR_MISALIGNED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (concat_splits(d)) {
+    EmbedParams pt, pb;
+    split_params(d, pt, pb);
+    for (EmbedParams* q : {&pt, &pb}) {
+      q->tok = tok; q->ids = byte_ids; q->ttb = ttb; q->E_tok = E_tok; q->E_byte = E_byte; q->lam = lam; q->out = out;
+      if (int rc = d->dtype == MOT_BF16 ? dispatch_fwd_bf16(*q, s) : dispatch_fwd_f32(*q, s)) return rc;
+    }
+    return MOT_OK;
+  }
   EmbedParams p;
   fill_params(d, p);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam; p.out = out;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return d->dtype == MOT_BF16 ? dispatch_fwd_bf16(p, s) : dispatch_fwd_f32(p, s);
 }
 
@@ -331,7 +366,20 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
     if (cudaMemsetAsync(reinterpret_cast<char*>(workspace) + w.byte_acc, 0, w.zero_end - w.byte_acc, s) != cudaSuccess)
       return check_launch();
   }
-  int rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
+  int rc = MOT_OK;
+  if (concat_splits(d)) {
+    EmbedParams pt, pb;
+    split_params(d, pt, pb);
+    for (EmbedParams* q : {&pt, &pb}) {
+      bind_ws(*q, w, workspace);
+      q->tok = tok; q->ids = byte_ids; q->ttb = ttb; q->E_tok = E_tok; q->E_byte = E_byte; q->lam = lam;
+      q->gout = grad_out; q->gE_tok = gE_tok; q->gE_byte = gE_byte; q->g_lam = g_lam;
+      q->R = p.R;  // one stream chunking for both halves and the finalize pass
+      if ((rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(*q, s) : dispatch_bwd_f32(*q, s))) return rc;
+    }
+  } else {
+    rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
+  }
   if (rc) return rc;
   int sms = 0, optin = 0;
   device_props(&sms, &optin);

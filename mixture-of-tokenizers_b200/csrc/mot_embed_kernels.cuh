@@ -55,6 +55,8 @@ struct EmbedParams {
   float* byte_acc;  // [n_rep, Vb*bd] fp32, zeroed per call
   float* lam_acc;   // [2]
   long long N, T;
+  long long io_ld;  // row stride (elements) of `out` (forward) / `gout` (backward); Do unless the call is one half of a split concat
+  int io_col;       // first column of this kernel's slice inside those rows
   int V, Vb, bpt, Dt, bd, Do, combine, flags, ttb_dtype;
   int n_chunks;  // Do / 8
   int R;         // stream entries per chunk (multiple of 32)
@@ -161,34 +163,41 @@ __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s,
   return s.kind == 1 ? (int)__ldg(reinterpret_cast<const long long*>(a)) : __ldg(reinterpret_cast<const int*>(a));
 }
 
-// Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all
-// variants); MODE 1: the MoT-sum fast path (runs/71): combine == ADD, out_norm only, no lambdas.
+// Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all variants);
+// MODE 1: the MoT-sum fast path (runs/71): combine == ADD, out_norm only, no lambdas;
+// MODE 2 / 3: the two halves of the split [tok | bytes] concat operand of the projection variants (runs/7:226-232):
+//   2 = tok-only rows with the per-input token norm, 3 = bytes-only rows with the per-byte norm (neither has a norm
+//   over the mixed row, so the backward needs no reduction and keeps nothing of the row in registers).
 template <int MODE>
 struct Cfg {
-  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 0 && (p.flags & MOT_F_TOK_NORM); }
+  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 2 || (MODE == 0 && (p.flags & MOT_F_TOK_NORM)); }
   __device__ __forceinline__ static bool byte_scale(const EmbedParams& p) {
-    return MODE == 0 && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN);
+    return MODE == 3 || (MODE == 0 && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN));
   }
   __device__ __forceinline__ static bool has_lam(const EmbedParams& p) { return MODE == 0 && (p.flags & MOT_F_HAS_LAMBDAS); }
-  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (p.flags & MOT_F_OUT_NORM); }
-  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || p.combine != MOT_BYTES_ONLY; }
-  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || p.combine != MOT_TOK_ONLY; }
+  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (MODE == 0 && (p.flags & MOT_F_OUT_NORM)); }
+  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || MODE == 2 || (MODE == 0 && p.combine != MOT_BYTES_ONLY); }
+  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || MODE == 3 || (MODE == 0 && p.combine != MOT_TOK_ONLY); }
   __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MODE == 0 && p.combine == MOT_MEAN; }
 };
 inline int pick_mode(const EmbedParams& p, int cw) {
   const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
-  return (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.Do % (32 * cw) == 0 && p.tab_smem) ? 1 : 0;
+  if (p.Do % (32 * cw) != 0) return 0;
+  if (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.tab_smem) return 1;
+  if (p.combine == MOT_TOK_ONLY && f == MOT_F_TOK_NORM) return 2;
+  if (p.combine == MOT_BYTES_ONLY && f == MOT_F_BYTE_NORM && p.tab_smem) return 3;
+  return 0;
 }
 
-#define MOT_TOK_OK(it) (MODE == 1 || cm[it].toff >= 0)
-#define MOT_BYTE_OK(it) (MODE == 1 || cm[it].slot >= 0)
+#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || (MODE == 0 && cm[it].toff >= 0))
+#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || (MODE == 0 && cm[it].slot >= 0))
 // element offset of chunk `it` in the token row: affine (base + immediate addressing) on the fast path
-#define MOT_TOFF(it) (MODE == 1 ? ((it) * 32 + lane) * CW : cm[it].toff)
-#define MOT_CHUNK_OK(it) (MODE == 1 || ((it) * 32 + lane) * CW < p.Do)
+#define MOT_TOFF(it) ((MODE == 1 || MODE == 2) ? ((it) * 32 + lane) * CW : cm[it].toff)
+#define MOT_CHUNK_OK(it) (MODE != 0 || ((it) * 32 + lane) * CW < p.Do)
 
 template <typename T, int MODE = 0, int CW = 8>
 __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
-  if (MODE == 1) return Vec<T, CW>::lds_raw(tab + off);  // the fast path is only dispatched when the table fits
+  if (MODE == 1 || MODE == 3) return Vec<T, CW>::lds_raw(tab + off);  // fast paths are only dispatched when the table fits
   return p.tab_smem ? Vec<T, CW>::lds_raw(tab + off) : Vec<T, CW>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
@@ -267,8 +276,8 @@ __device__ __forceinline__ void gmem_add4(float* a, const float (&v)[4]) {
 // ======================================================================================
 // Forward
 // ======================================================================================
-template <typename T, int CPL, int MODE>
-__global__ void __launch_bounds__(1024, 1) mot_fwd_kernel(const EmbedParams p) {
+template <typename T, int CPL, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
   using C = Cfg<MODE>;
   constexpr int CW = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(1024, 1) mot_fwd_kernel(const EmbedParams p) {
       s = 0;
       parity ^= 1u;
     }
-    T* orow = out + (size_t)pos * p.Do;
+    T* orow = out + (size_t)pos * p.io_ld + p.io_col;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
       if (MOT_CHUNK_OK(it)) {
@@ -597,7 +606,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       const int pos = iw ? B.pos : A.pos, v = iw ? B.v : A.v;
       unsigned char* st = ring + (size_t)is * L.stage_bytes;
       mbar_expect_tx(bars + is, g_bytes + t_bytes);
-      bulk_g2s(st, gout + (size_t)pos * p.Do, g_bytes, bars + is);
+      bulk_g2s(st, gout + (size_t)pos * p.io_ld + p.io_col, g_bytes, bars + is);
       if (has_tok) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + is);
     }
     ++issued;
@@ -730,8 +739,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) idv[it] = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
       // z = tscale * t + lam_b * rs * b
-      float z[CPL][CW], gr[CPL][CW];  // mixed row and upstream gradient row of this occurrence
+      float z[CPL][CW], gr[CPL][CW];  // mixed row and upstream gradient row of this occurrence (only with out_norm)
       float ss = 0.f, gz = 0.f;
+      if (out_norm) {
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (has_tok && MOT_TOK_OK(it)) {
@@ -774,17 +784,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         }
         if (MOT_CHUNK_OK(it)) {
           V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), gr[it]);
-          if (out_norm) {
 #pragma unroll
-            for (int e = 0; e < CW; ++e) {
-              ss += z[it][e] * z[it][e];
-              gz += gr[it][e] * z[it][e];
-            }
+          for (int e = 0; e < CW; ++e) {
+            ss += z[it][e] * z[it][e];
+            gz += gr[it][e] * z[it][e];
           }
         } else {
 #pragma unroll
           for (int e = 0; e < CW; ++e) gr[it][e] = 0.f;
         }
+      }
       }
       float r_o = 1.f, coef = 0.f;
       if (out_norm) {
@@ -797,8 +806,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         const bool valid = MOT_CHUNK_OK(it);  // lane-dependent: no warp collectives under it
         float dz[CW];
         if (valid) {
+          if (out_norm) {
 #pragma unroll
-          for (int e = 0; e < CW; ++e) dz[e] = out_norm ? r_o * gr[it][e] - coef * z[it][e] : gr[it][e];
+            for (int e = 0; e < CW; ++e) dz[e] = r_o * gr[it][e] - coef * z[it][e];
+          } else {  // no norm over the mixed row: dz is the upstream gradient itself
+            V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), dz);
+          }
           if (MOT_TOK_OK(it)) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) Du[it][e] += dz[e];
@@ -1026,9 +1039,12 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
-  // widest CTA whose per-warp ring (>= 2 stages) fits next to the byte table: 32, 16 or 8 warps
+  // Rows up to 3 x 256 elements: compiled for <= 64 registers, launched with 24 warps.  Wider rows hold more of the
+  // row per lane: compiled for <= 128 registers, 16 warps (no spills; measured as fast at 1024 elements).
+  constexpr int NT = CPL * sizeof(T) <= 6 ? 1024 : 512;
   static const char* env_thr = getenv("MOT_FWD_THREADS");  // debug knob
-  int threads = env_thr ? atoi(env_thr) : kFwdThreads;
+  int threads = env_thr ? atoi(env_thr) : (NT == 1024 ? kFwdThreads : 512);
+  if (threads > NT) threads = NT;
   size_t smem = 0;
   for (; threads >= 256; threads = threads > 512 ? threads - 256 : threads >> 1) {
     smem = plan_smem(p, sizeof(T), threads / 32, false, optin);
@@ -1036,7 +1052,7 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   }
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
   if (MODE == 1 && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
-  auto kern = mot_fwd_kernel<T, CPL, MODE>;
+  auto kern = mot_fwd_kernel<T, CPL, MODE, NT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   const long long warps_needed = p.N;
   long long blocks = (warps_needed + (threads / 32) - 1) / (threads / 32);
@@ -1056,7 +1072,7 @@ static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   EmbedParams p = p_in;
   const size_t smem = plan_smem(p, sizeof(T), kBwdThreads / 32, true, optin);
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
-  if (MODE == 1 && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
+  if ((MODE == 1 || MODE == 3) && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
   auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
@@ -1071,6 +1087,7 @@ int dispatch_fwd_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_fwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
+int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
 int launch_finalize_bf16(const EmbedParams& p, int blocks, cudaStream_t s);
 int launch_finalize_f32(const EmbedParams& p, int blocks, cudaStream_t s);
 
