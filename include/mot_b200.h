@@ -107,6 +107,12 @@ void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* 
 int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
                    int32_t ttb_dtype, void* out, int32_t out_i64, void* stream);
 
+/* tokens -> padded digit ids, the arithmetic ttb analogue of mathblations (GenerateEquations.tokens_to_digits,
+ * mathblations/data.py:92-109): decimal digits right-aligned in dpt slots, pad 13; op / eq / pad tokens -> 10 / 11 / 12
+ * in the last slot.  tok int32 or int64 (tok_i64), out [n, dpt] int32 or int64 (out_i64). */
+int mot_tokens_to_digits(const void* tok, int64_t n, int32_t tok_i64, int32_t dpt, int64_t op_token, int64_t eq_token,
+                         int64_t pad_token, void* out, int32_t out_i64, void* stream);
+
 /* Workspace needed by mot_embed_bwd for this descriptor (bytes, 256-aligned). */
 size_t mot_embed_workspace_bytes(const MotDesc* d);
 
@@ -162,21 +168,26 @@ int mot_pull(const void* bytes_in, void* bytes_out, int64_t n_rows, int64_t toke
              size_t ws_bytes, void* stream);
 
 /* ---- dense projection of the concat+projection variants (tcgen05 tensor cores) -------------------------------
- * bf16 operands, fp32 accumulation in tensor memory.  in_dim = tok_dim + bpt*byte_dim (the row width of the
+ * dtype = MOT_BF16: bf16 operands (kind::f16); MOT_F32: fp32 operands read in place on the TF32 path (kind::tf32, the
+ * precision mathblations selects with set_float32_matmul_precision('high'), main.py:522); fp32 accumulation in tensor
+ * memory either way.  in_dim = tok_dim + bpt*byte_dim (the row width of the
  * [tok | bytes] operand mot_embed_fwd produces with MOT_CONCAT), out_dim = model_dim; both multiples of 8. */
 
 /* y[n_tokens, out_dim] = x[n_tokens, in_dim] . w[out_dim, in_dim]^T (+ bias[out_dim], fp32, or NULL).
  * Replaces F.linear of mixin_bytes (runs/7:233-234), CastedLinear (spt/train_gpt.py:185-186,443) and
- * DigitMixinConcat.fc (mathblations/model.py:261,268).  y is bf16, or fp32 when y_f32 != 0. */
+ * DigitMixinConcat.fc (mathblations/model.py:261,268).  y is bf16, or fp32 when y_f32 != 0 (always with MOT_F32). */
 int mot_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t n_tokens, int32_t in_dim,
-                   int32_t out_dim, int32_t y_f32, void* stream);
+                   int32_t out_dim, int32_t dtype, int32_t y_f32, void* stream);
 /* dx[n_tokens, in_dim] = dy[n_tokens, out_dim] . w[out_dim, in_dim]   (autograd of F.linear w.r.t. its input) */
+/* The two backward products read bf16 operands in place; with MOT_F32 they run on transposed fp32 copies built in a
+ * caller-provided workspace of mot_linear_workspace_bytes() bytes (0 for bf16: pass NULL). */
+size_t mot_linear_workspace_bytes(int64_t n_tokens, int32_t in_dim, int32_t out_dim, int32_t dtype);
 int mot_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t n_tokens, int32_t in_dim, int32_t out_dim,
-                         void* stream);
+                         int32_t dtype, void* workspace, size_t ws_bytes, void* stream);
 /* dw[out_dim, in_dim] = dy^T . x, reduced in fp32 into dw_f32 (overwritten; the fp32 master-weight gradient of
  * spt/train_gpt.py:1155-1156) and, when dw_bf16 != NULL, also cast to bf16 (the bf16 mixin weight of runs/7:249). */
 int mot_linear_bwd_weight(const void* dy, const void* x, float* dw_f32, void* dw_bf16, int64_t n_tokens, int32_t in_dim,
-                          int32_t out_dim, void* stream);
+                          int32_t out_dim, int32_t dtype, void* workspace, size_t ws_bytes, void* stream);
 
 /* Row-wise rms_norm without weight (F.rms_norm(x, (x.size(-1),)), spt/train_gpt.py:172-173) over [n_rows, dim] and
  * its backward dy = rs*g - y*rs^3*mean(g.y): the `norm(...)` around the projection (runs/7:234, train_gpt.py:443). */

@@ -20,10 +20,13 @@
 namespace mot {
 
 constexpr int kGemmThreads = 256;
-constexpr int BM = 128, BN = 256, BK = 64;  // CTA tile; BK * 2 B = one 128-byte swizzle row
-constexpr int UMMA_K = 16;                  // bf16: 32 bytes of contraction per tcgen05.mma
+// CTA tile 128 x 256 x (128 bytes of contraction): one 128-byte swizzle row = 64 bf16 or 32 fp32 (tf32) elements, and
+// one tcgen05.mma consumes 32 bytes of it (K = 16 for kind::f16, K = 8 for kind::tf32), so both element types share
+// the stage layout, the byte offsets of the descriptors and four MMAs per stage.
+constexpr int BM = 128, BN = 256;
+constexpr int kRowBytes = 128, kMmaBytes = 32;
 constexpr int kGemmStages = 4;
-constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kABytes = BM * kRowBytes, kBBytes = BN * kRowBytes, kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kTmemCols = 512;  // two fp32 accumulators of BN columns
 
 enum { EPI_STORE_BF16 = 0, EPI_STORE_F32 = 1, EPI_RED_F32 = 2 };
@@ -33,7 +36,7 @@ struct GemmParams {
   const float* bias;  // [N] fp32 or null (added in the epilogue)
   long long ldc;
   int M, N, K;
-  int m_tiles, n_tiles, k_blocks;  // k_blocks = ceil(K / BK)
+  int m_tiles, n_tiles, k_blocks;  // k_blocks = ceil(K / elements per 128-byte row)
   int splits;                      // split of the contraction range (EPI_RED_F32 only)
 };
 
@@ -55,15 +58,27 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -100,10 +115,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, operand majors, N, M
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, operand format (1 = bf16, 2 = tf32), operand
+// majors, N, M
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct __align__(8) GemmBarriers {
@@ -111,7 +127,8 @@ struct __align__(8) GemmBarriers {
   uint32_t tmem_base;
 };
 
-template <bool A_MN, bool B_MN, int EPI>
+// TE: operand element type (__nv_bfloat16 -> kind::f16, float -> kind::tf32, fp32 values read in place)
+template <typename TE, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -119,6 +136,9 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   unsigned char* stage_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_base + (size_t)kGemmStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = lane_id();
+  constexpr bool kTf32 = sizeof(TE) == 4;
+  constexpr int KE = kRowBytes / sizeof(TE);     // contraction elements per stage (one 128-byte swizzle row): 64 / 32
+  constexpr int kMnBlock = KE * kRowBytes;       // MN-major operand: one block = KE contraction rows x 128 B of MN elements
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
@@ -157,17 +177,17 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           unsigned char* sa = stage_base + (size_t)stage * kStageBytes;
           unsigned char* sb = sa + kABytes;
           mbar_expect_tx(&bars->full[stage], kStageBytes);
-          if (A_MN) {  // global [K rows][M cols]: one box of 64 M-elements x BK k-rows per 64-wide MN block
+          if (A_MN) {  // global [K rows][M cols]: one box of KE M-elements (128 B) x KE k-rows per MN block
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, m_blk * BM + j * 64, kb * BK, &bars->full[stage]);
-          } else {     // global [M rows][K cols]: one box of BK k-elements x BM rows
-            tma_load_2d(sa, &tmap_a, kb * BK, m_blk * BM, &bars->full[stage]);
+            for (int j = 0; j < BM / KE; ++j) tma_load_2d(sa + j * kMnBlock, &tmap_a, m_blk * BM + j * KE, kb * KE, &bars->full[stage]);
+          } else {     // global [M rows][K cols]: one box of KE k-elements (128 B) x BM rows
+            tma_load_2d(sa, &tmap_a, kb * KE, m_blk * BM, &bars->full[stage]);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, n_blk * BN + j * 64, kb * BK, &bars->full[stage]);
+            for (int j = 0; j < BN / KE; ++j) tma_load_2d(sb + j * kMnBlock, &tmap_b, n_blk * BN + j * KE, kb * KE, &bars->full[stage]);
           } else {
-            tma_load_2d(sb, &tmap_b, kb * BK, n_blk * BN, &bars->full[stage]);
+            tma_load_2d(sb, &tmap_b, kb * KE, n_blk * BN, &bars->full[stage]);
           }
           if (++stage == kGemmStages) {
             stage = 0;
@@ -179,7 +199,8 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BM, BN);
+      constexpr uint32_t idesc = make_idesc(kTf32, A_MN, B_MN, BM, BN);
+      constexpr int kMmaRows = kMmaBytes / sizeof(TE);  // contraction rows per MMA of an MN-major operand: 16 / 8
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -194,11 +215,11 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes), sb = sa + kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance along the contraction: 32 B inside the swizzle row (K-major) / 16 k-rows = 2 KB (MN-major)
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BK * 128, 1024) : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BK * 128, 1024) : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kRowBytes / kMmaBytes; ++k) {
+            // advance along the contraction: 32 B inside the swizzle row (K-major) / 16 or 8 k-rows of 128 B (MN-major)
+            const uint64_t da = A_MN ? make_desc(sa + k * (kMmaRows * kRowBytes), kMnBlock, 1024) : make_desc(sa + k * kMmaBytes, 16, 1024);
+            const uint64_t db = B_MN ? make_desc(sb + k * (kMmaRows * kRowBytes), kMnBlock, 1024) : make_desc(sb + k * kMmaBytes, 16, 1024);
+            umma<kTf32>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&bars->empty[stage]);  // frees the stage once these MMAs have read it
           if (++stage == kGemmStages) {
@@ -356,6 +377,22 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
   }
 }
 
+// dst[c][r] = src[r][c] for fp32 (32 x 32 tiles through shared memory).  Only the fp32 (TF32) backward uses it: the
+// hardware's MN-major operand layout for 32-bit elements is a different swizzle atom than the 16-bit one this kernel
+// stages with TMA, so the two small fp32 backward GEMMs (mathblations: 11 K tokens) run on transposed copies instead.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C, long long ld_dst) {
+  __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (r0 + j < R && c0 + tx < C) tile[j][tx] = src[(size_t)(r0 + j) * C + c0 + tx];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+    if (c0 + j < C && r0 + tx < R) dst[(size_t)(c0 + j) * ld_dst + r0 + tx] = tile[tx][j];
+}
+
 // ======================================================================================
 // Host side
 // ======================================================================================
@@ -374,15 +411,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 matrix [rows][cols] row-major (cols contiguous); box = box_cols x box_rows, 128-byte swizzle, zero fill out of bounds
-static int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, int box_cols, int box_rows) {
+// matrix [rows][cols] row-major (cols contiguous) of bf16 (esz 2) or fp32 (esz 4); box = box_cols x box_rows, 128-byte
+// swizzle, zero fill out of bounds
+static int make_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, int box_cols, int box_rows, int esz,
+                     long long ld = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return MOT_ERR_CUDA;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * esz};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  const CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MOT_OK : MOT_ERR_BAD_ARG;
@@ -390,22 +429,23 @@ static int make_tmap(CUtensorMap* m, const void* base, long long rows, long long
 
 // C[M,N] (+)= op(A) . op(B)^T with the contraction dimension of length K.
 //   a_mn == false: A is [M][K] row-major;  true: A is [K][M] row-major.  Same for B with N.
-template <bool A_MN, bool B_MN, int EPI>
+template <typename TE, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long ldc, int splits,
-                       cudaStream_t s) {
+                       cudaStream_t s, long long lda = 0, long long ldb = 0) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
+  constexpr int ES = sizeof(TE), KE = kRowBytes / ES;
   CUtensorMap ta, tb;
-  if (int rc = A_MN ? make_tmap(&ta, A, K, M, 64, BK) : make_tmap(&ta, A, M, K, BK, BM)) return rc;
-  if (int rc = B_MN ? make_tmap(&tb, B, K, N, 64, BK) : make_tmap(&tb, B, N, K, BK, BN)) return rc;
+  if (int rc = A_MN ? make_tmap(&ta, A, K, M, KE, KE, ES, lda) : make_tmap(&ta, A, M, K, KE, BM, ES, lda)) return rc;
+  if (int rc = B_MN ? make_tmap(&tb, B, K, N, KE, KE, ES, ldb) : make_tmap(&tb, B, N, K, KE, BN, ES, ldb)) return rc;
   GemmParams p{};
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
-  p.k_blocks = (K + BK - 1) / BK;
+  p.k_blocks = (K + KE - 1) / KE;
   p.splits = splits < 1 ? 1 : splits;
   const size_t smem = (size_t)kGemmStages * kStageBytes + sizeof(GemmBarriers) + 1024;
-  auto kern = mot_gemm_kernel<A_MN, B_MN, EPI>;
+  auto kern = mot_gemm_kernel<TE, A_MN, B_MN, EPI>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   long long work = (long long)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(work < sms ? work : sms);
@@ -416,48 +456,86 @@ static int launch_gemm(const void* A, const void* B, void* C, const float* bias,
 
 static bool ok16(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+static void launch_transpose(const float* src, float* dst, int R, int C, long long ld_dst, cudaStream_t s) {
+  launch_pdl(transpose_f32_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0, s, src, dst, R, C, ld_dst);
+  count_launch();
+}
+static long long pad4(long long n) { return (n + 3) / 4 * 4; }
+
 }  // namespace mot
 
 using namespace mot;
 
 extern "C" int mot_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t n_tokens, int32_t in_dim,
-                              int32_t out_dim, int32_t y_f32, void* stream) {
+                              int32_t out_dim, int32_t dtype, int32_t y_f32, void* stream) {
   if (n_tokens < 0 || n_tokens > 0x7fffffffLL || in_dim <= 0 || out_dim <= 0) return MOT_ERR_BAD_ARG;
+  if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
+  if (dtype == MOT_F32 && !y_f32) return MOT_ERR_UNSUPPORTED;
   if (in_dim % 8 || out_dim % 8) return MOT_ERR_MISALIGNED;
   if (n_tokens == 0) return MOT_OK;
   if (!ok16(x) || !ok16(w) || !ok16(y)) return x && w && y ? MOT_ERR_MISALIGNED : MOT_ERR_BAD_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return y_f32 ? launch_gemm<false, false, EPI_STORE_F32>(x, w, y, bias, (int)n_tokens, out_dim, in_dim, out_dim, 1, s)
-               : launch_gemm<false, false, EPI_STORE_BF16>(x, w, y, bias, (int)n_tokens, out_dim, in_dim, out_dim, 1, s);
+  const int n = (int)n_tokens;
+  if (dtype == MOT_F32) return launch_gemm<float, false, false, EPI_STORE_F32>(x, w, y, bias, n, out_dim, in_dim, out_dim, 1, s);
+  return y_f32 ? launch_gemm<__nv_bfloat16, false, false, EPI_STORE_F32>(x, w, y, bias, n, out_dim, in_dim, out_dim, 1, s)
+               : launch_gemm<__nv_bfloat16, false, false, EPI_STORE_BF16>(x, w, y, bias, n, out_dim, in_dim, out_dim, 1, s);
+}
+
+extern "C" size_t mot_linear_workspace_bytes(int64_t n_tokens, int32_t in_dim, int32_t out_dim, int32_t dtype) {
+  if (dtype != MOT_F32 || n_tokens <= 0 || in_dim <= 0 || out_dim <= 0) return 0;  // bf16 operands are read in place
+  const size_t wt = (size_t)in_dim * out_dim * 4;
+  const size_t acts = (size_t)pad4(n_tokens) * ((size_t)in_dim + out_dim) * 4;
+  return (wt > acts ? wt : acts) + 256;
 }
 
 extern "C" int mot_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t n_tokens, int32_t in_dim, int32_t out_dim,
-                                    void* stream) {
+                                    int32_t dtype, void* workspace, size_t ws_bytes, void* stream) {
   if (n_tokens < 0 || n_tokens > 0x7fffffffLL || in_dim <= 0 || out_dim <= 0) return MOT_ERR_BAD_ARG;
+  if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
   if (in_dim % 8 || out_dim % 8) return MOT_ERR_MISALIGNED;
   if (n_tokens == 0) return MOT_OK;
   if (!ok16(dy) || !ok16(w) || !ok16(dx)) return dy && w && dx ? MOT_ERR_MISALIGNED : MOT_ERR_BAD_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == MOT_F32) {  // dX = dY . (W^T)^T with W^T [K, Do] built in the workspace
+    if (!workspace || ws_bytes < mot_linear_workspace_bytes(n_tokens, in_dim, out_dim, dtype)) return MOT_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MOT_ERR_MISALIGNED;
+    float* wt = reinterpret_cast<float*>(workspace);
+    launch_transpose(reinterpret_cast<const float*>(w), wt, out_dim, in_dim, out_dim, s);
+    return launch_gemm<float, false, false, EPI_STORE_F32>(dy, wt, dx, nullptr, (int)n_tokens, in_dim, out_dim, in_dim, 1, s);
+  }
   // dX[n, K] = dY[n, Do] . W[Do, K]: contraction over Do; dY is K-major, W is read in place as an MN-major operand
-  return launch_gemm<false, true, EPI_STORE_BF16>(dy, w, dx, nullptr, (int)n_tokens, in_dim, out_dim, in_dim, 1,
-                                                  reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm<__nv_bfloat16, false, true, EPI_STORE_BF16>(dy, w, dx, nullptr, (int)n_tokens, in_dim, out_dim, in_dim, 1, s);
 }
 
 extern "C" int mot_linear_bwd_weight(const void* dy, const void* x, float* dw_f32, void* dw_bf16, int64_t n_tokens, int32_t in_dim,
-                                     int32_t out_dim, void* stream) {
+                                     int32_t out_dim, int32_t dtype, void* workspace, size_t ws_bytes, void* stream) {
   if (n_tokens < 0 || n_tokens > 0x7fffffffLL || in_dim <= 0 || out_dim <= 0) return MOT_ERR_BAD_ARG;
+  if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
   if (in_dim % 8 || out_dim % 8) return MOT_ERR_MISALIGNED;
   if (!dw_f32 || (reinterpret_cast<uintptr_t>(dw_f32) & 15u)) return MOT_ERR_BAD_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t n_el = (size_t)out_dim * in_dim;
+  if (dtype == MOT_F32 && n_tokens > 0) {  // dW = (dY^T) . (X^T)^T on transposed copies [Do, n] and [K, n] in the workspace
+    if (!ok16(dy) || !ok16(x)) return dy && x ? MOT_ERR_MISALIGNED : MOT_ERR_BAD_ARG;
+    if (!workspace || ws_bytes < mot_linear_workspace_bytes(n_tokens, in_dim, out_dim, dtype)) return MOT_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return MOT_ERR_MISALIGNED;
+    const long long ld = pad4(n_tokens);
+    float* dyT = reinterpret_cast<float*>(workspace);
+    float* xT = dyT + (size_t)out_dim * ld;
+    launch_transpose(reinterpret_cast<const float*>(dy), dyT, (int)n_tokens, out_dim, ld, s);
+    launch_transpose(reinterpret_cast<const float*>(x), xT, (int)n_tokens, in_dim, ld, s);
+    return launch_gemm<float, false, false, EPI_STORE_F32>(dyT, xT, dw_f32, nullptr, out_dim, in_dim, (int)n_tokens, in_dim, 1, s, ld, ld);
+  }
   if (cudaMemsetAsync(dw_f32, 0, n_el * 4, s) != cudaSuccess) return check_launch();
   if (n_tokens > 0) {
     if (!ok16(dy) || !ok16(x)) return dy && x ? MOT_ERR_MISALIGNED : MOT_ERR_BAD_ARG;
     int sms = 0, optin = 0;
     if (int rc = device_props(&sms, &optin)) return rc;
     // dW[Do, K] = dY^T . X: contraction over the tokens, both operands MN-major; split the token range so that the
-    // tiles x splits fill the machine (at least 4 k-blocks of 64 tokens per split)
+    // tiles x splits fill the machine (at least 4 k-blocks per split)
     const int tiles = ((out_dim + BM - 1) / BM) * ((in_dim + BN - 1) / BN);
-    const long long kblocks = (n_tokens + BK - 1) / BK;
+    const int ke = dtype == MOT_F32 ? kRowBytes / 4 : kRowBytes / 2;
+    const long long kblocks = (n_tokens + ke - 1) / ke;
     // pick the split count (<= 16, >= 4 k-blocks each) whose work items fill whole waves of the persistent grid best
     long long splits = 1;
     double best = 0.0;
@@ -469,7 +547,8 @@ extern "C" int mot_linear_bwd_weight(const void* dy, const void* x, float* dw_f3
         splits = sp;
       }
     }
-    if (int rc = launch_gemm<true, true, EPI_RED_F32>(dy, x, dw_f32, nullptr, out_dim, in_dim, (int)n_tokens, in_dim, (int)splits, s))
+    if (int rc = launch_gemm<__nv_bfloat16, true, true, EPI_RED_F32>(dy, x, dw_f32, nullptr, out_dim, in_dim, (int)n_tokens, in_dim,
+                                                                     (int)splits, s))
       return rc;
   }
   if (dw_bf16) {  // the runs keep the mixin weight in bf16 (runs/7:249): cast the reduced gradient once

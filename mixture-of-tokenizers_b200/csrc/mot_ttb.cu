@@ -58,7 +58,52 @@ static int launch_expand(const int32_t* tok, long long n, const void* ttb, int V
   return check_launch();
 }
 
+// mathblations analogue of the ttb expansion, computed arithmetically (mathblations/data.py:92-109): a number token
+// becomes its decimal digits right-aligned in dpt slots padded with 13; the operator / equals / pad tokens become
+// 10 / 11 / 12 in the last slot.
+template <typename TokT, typename OutT>
+__global__ void __launch_bounds__(256) tokens_to_digits_kernel(const TokT* __restrict__ tok, long long n, int dpt, long long op_token,
+                                                              long long eq_token, long long pad_token, OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long t = (long long)tok[i];
+    OutT* o = out + i * dpt;
+    const int special = t == op_token ? 10 : (t == eq_token ? 11 : (t == pad_token ? 12 : -1));
+    for (int j = dpt - 1; j >= 0; --j) {
+      int d = 13;
+      if (special >= 0) {
+        if (j == dpt - 1) d = special;
+      } else if (j == dpt - 1 || t > 0) {  // "0" is one digit; leading positions stay pad
+        d = (int)(t % 10);
+        t /= 10;
+      }
+      o[j] = (OutT)d;
+    }
+  }
+}
+
 }  // namespace mot
+
+extern "C" int mot_tokens_to_digits(const void* tok, int64_t n, int32_t tok_i64, int32_t dpt, int64_t op_token, int64_t eq_token,
+                                    int64_t pad_token, void* out, int32_t out_i64, void* stream) {
+  if (n < 0 || dpt <= 0) return MOT_ERR_BAD_ARG;
+  if (n == 0) return MOT_OK;
+  if (!tok || !out) return MOT_ERR_BAD_ARG;
+  int sms = 0, optin = 0;
+  if (int rc = mot::device_props(&sms, &optin)) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  long long blocks = (n + 255) / 256;
+  if (blocks > sms * 8LL) blocks = sms * 8LL;
+  const dim3 g((unsigned)blocks), b(256);
+  using namespace mot;
+  if (tok_i64 && out_i64) launch_pdl(tokens_to_digits_kernel<long long, long long>, g, b, 0, s, (const long long*)tok, (long long)n, (int)dpt, (long long)op_token, (long long)eq_token, (long long)pad_token, (long long*)out);
+  else if (tok_i64) launch_pdl(tokens_to_digits_kernel<long long, int>, g, b, 0, s, (const long long*)tok, (long long)n, (int)dpt, (long long)op_token, (long long)eq_token, (long long)pad_token, (int*)out);
+  else if (out_i64) launch_pdl(tokens_to_digits_kernel<int, long long>, g, b, 0, s, (const int*)tok, (long long)n, (int)dpt, (long long)op_token, (long long)eq_token, (long long)pad_token, (long long*)out);
+  else launch_pdl(tokens_to_digits_kernel<int, int>, g, b, 0, s, (const int*)tok, (long long)n, (int)dpt, (long long)op_token, (long long)eq_token, (long long)pad_token, (int*)out);
+  count_launch();
+  return check_launch();
+}
 
 extern "C" int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
                               int32_t ttb_dtype, void* out, int32_t out_i64, void* stream) {

@@ -171,3 +171,29 @@ class SptByteMixEmbedding(nn.Module):
         x = mot_embed_proj(tokens, ids, self.embed.embed_tokens.weight, self.embed.embed_bytes.weight,
                            self.byte_mixin.mixin.mixin.weight, self.spec, bpt=self.bpt)
         return x.view(B, S, -1)
+
+
+class DigitMixinEmbedding(nn.Module):
+    """mathblations' `wte` + `dte` + `DigitMixinConcat` (mathblations/model.py:304-305,256-268,323-327) fused behind one
+    call: forward(idx [B,S] int64, digits [B, S*dpt] int64) -> `digit_mixin(wte(idx), dte(digits))` = fc([digits | tok])
+    with bias, no norms, fp32 parameters on the TF32 tensor-core path (main.py:522 sets matmul precision 'high').
+    State-dict keys as in the reference GPT: `wte.weight`, `dte.weight`, `digit_mixin.fc.weight`, `digit_mixin.fc.bias`.
+    `digit_mixin_method="cross_attn"` and `use_digit_self_attn` are refused (attention, not a gather/pool)."""
+
+    def __init__(self, vocab_size: int, n_embd_tok: int, n_embd_digit: int, length_factor: int,
+                 digit_mixin_method: str = "concat", use_digit_self_attn: bool = False, n_digit_vocab: int = 14):
+        super().__init__()
+        if digit_mixin_method != "concat" or use_digit_self_attn:
+            raise NotImplementedError("mot_b200: only the concat digit mixin without digit self-attention has a kernel")
+        self.dpt = length_factor
+        self.wte = nn.Embedding(vocab_size, n_embd_tok)
+        self.dte = nn.Embedding(n_digit_vocab, n_embd_digit)
+        self.digit_mixin = _Holder()
+        self.digit_mixin.fc = nn.Linear(n_embd_tok + n_embd_digit * length_factor, n_embd_tok)
+        self.spec = MixSpec(combine="concat", out_norm=False, bytes_first=True)
+
+    def forward(self, idx: torch.Tensor, digits: torch.Tensor) -> torch.Tensor:
+        B, S = idx.shape
+        x = mot_embed_proj(idx, digits, self.wte.weight, self.dte.weight, self.digit_mixin.fc.weight, self.spec,
+                           bpt=self.dpt, bias=self.digit_mixin.fc.bias)
+        return x.view(B, S, -1)

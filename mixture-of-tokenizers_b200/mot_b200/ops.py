@@ -95,6 +95,22 @@ def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype =
     return out.view(1, -1)
 
 
+def tokens_to_digits(tokens: torch.Tensor, max_digits_per_token: int, op_token: int, eq_token: int, pad_token: int,
+                     out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """GenerateEquations.tokens_to_digits (mathblations/data.py:92-109) on the device: [n] -> [n * dpt]."""
+    dev = _require_cuda(tokens)
+    if tokens.dtype not in (torch.int32, torch.int64) or out_dtype not in (torch.int32, torch.int64):
+        raise NotImplementedError("mot_b200.tokens_to_digits: int32 / int64 only")
+    t = tokens.reshape(-1).contiguous()
+    out = torch.empty(t.numel() * max_digits_per_token, dtype=out_dtype, device=dev)
+    with _on_device(dev):
+        rc = L.lib().mot_tokens_to_digits(_ptr(t), t.numel(), 1 if t.dtype == torch.int64 else 0, max_digits_per_token,
+                                          op_token, eq_token, pad_token, _ptr(out), 1 if out_dtype == torch.int64 else 0,
+                                          _stream(dev))
+    L.check(rc, "mot_tokens_to_digits")
+    return out
+
+
 def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_byte: int, from_right: bool) -> torch.Tensor:
     dev = _require_cuda(byte_tensor)
     if byte_tensor.dtype not in (torch.int32, torch.int64) or byte_tensor.dim() != 2:
@@ -381,40 +397,54 @@ def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], 
 # ------------------------------------------------------------------------------------------------------------
 # concat + dense projection variants (V1 runs/7:226-234,317-319 and spt/train_gpt.py:439-443; V2 runs/72:227-230)
 # ------------------------------------------------------------------------------------------------------------
-def _check_bf16(*ts):
-    for t in ts:
-        if t is not None and t.dtype != torch.bfloat16:
-            raise NotImplementedError("mot_b200: the tcgen05 projection kernels take bf16 operands "
-                                      f"(got {t.dtype}); fp32 tables are not supported on this path")
+def _gemm_dtype(*ts) -> int:
+    """Operand dtype of the projection kernels: all bf16 (kind::f16) or all fp32 (read in place on the TF32 path)."""
+    dts = {t.dtype for t in ts if t is not None}
+    if dts == {torch.bfloat16}:
+        return L.BF16
+    if dts == {torch.float32}:
+        return L.F32
+    raise NotImplementedError(f"mot_b200: the tcgen05 projection kernels take all-bf16 or all-fp32 operands, got {sorted(map(str, dts))}")
+
+
+def _linear_ws(n: int, in_dim: int, out_dim: int, dt: int, dev) -> Optional[torch.Tensor]:
+    need = int(L.lib().mot_linear_workspace_bytes(n, in_dim, out_dim, dt))
+    return torch.empty(need, dtype=torch.uint8, device=dev) if need else None
 
 
 def linear_forward_out(x, w, y, bias=None) -> None:
-    """y[n, Do] = x[n, K] . w[Do, K]^T (+ bias): mot_linear_fwd (tcgen05).  y is bf16 or fp32."""
-    _check_bf16(x, w)
+    """y[n, Do] = x[n, K] . w[Do, K]^T (+ bias): mot_linear_fwd (tcgen05).  bf16 operands -> y bf16 or fp32; fp32
+    operands (TF32 tensor cores) -> y fp32."""
+    dt = _gemm_dtype(x, w)
     dev = _require_cuda(x, w, y, bias)
     n, K = x.shape
+    if dt == L.F32 and y.dtype != torch.float32:
+        raise NotImplementedError("mot_b200: fp32 operands produce an fp32 result")
     with _on_device(dev):
-        rc = L.lib().mot_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, K, w.shape[0],
+        rc = L.lib().mot_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), n, K, w.shape[0], dt,
                                     1 if y.dtype == torch.float32 else 0, _stream(dev))
     L.check(rc, "mot_linear_fwd")
 
 
 def linear_bwd_input_out(dy, w, dx) -> None:
     """dx[n, K] = dy[n, Do] . w[Do, K]: mot_linear_bwd_input (w read in place as an MN-major operand)."""
-    _check_bf16(dy, w, dx)
+    dt = _gemm_dtype(dy, w, dx)
     dev = _require_cuda(dy, w, dx)
+    ws = _linear_ws(dy.shape[0], w.shape[1], w.shape[0], dt, dev)
     with _on_device(dev):
-        rc = L.lib().mot_linear_bwd_input(_ptr(dy), _ptr(w), _ptr(dx), dy.shape[0], w.shape[1], w.shape[0], _stream(dev))
+        rc = L.lib().mot_linear_bwd_input(_ptr(dy), _ptr(w), _ptr(dx), dy.shape[0], w.shape[1], w.shape[0], dt,
+                                          _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev))
     L.check(rc, "mot_linear_bwd_input")
 
 
 def linear_bwd_weight_out(dy, x, dw_f32, dw_bf16=None) -> None:
     """dw[Do, K] = dy^T . x reduced in fp32 (split over the tokens), optionally also cast to bf16."""
-    _check_bf16(dy, x, dw_bf16)
+    dt = _gemm_dtype(dy, x)
     dev = _require_cuda(dy, x, dw_f32, dw_bf16)
+    ws = _linear_ws(dy.shape[0], x.shape[1], dy.shape[1], dt, dev)
     with _on_device(dev):
         rc = L.lib().mot_linear_bwd_weight(_ptr(dy), _ptr(x), _ptr(dw_f32), _ptr(dw_bf16), dy.shape[0], x.shape[1],
-                                           dy.shape[1], _stream(dev))
+                                           dy.shape[1], dt, _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev))
     L.check(rc, "mot_linear_bwd_weight")
 
 
@@ -442,7 +472,9 @@ class _MotEmbedProjFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: MixSpec, bpt: int, tokens, byte_ids, E_tok, E_byte, W, bias):
         dev = _require_cuda(tokens, byte_ids, E_tok, E_byte, W, bias)
-        _check_bf16(E_tok, E_byte)
+        cdt = E_tok.dtype                      # compute dtype of the chain: bf16, or fp32 on the TF32 tensor-core path
+        if cdt not in (torch.bfloat16, torch.float32) or E_byte.dtype != cdt:
+            raise NotImplementedError("mot_b200: token and byte tables must both be bf16 or both fp32")
         tok = tokens.reshape(-1)
         tok = (tok if tok.dtype == torch.int32 else tok.to(torch.int32)).contiguous()
         if byte_ids.dtype not in (torch.int32, torch.int64):
@@ -457,14 +489,14 @@ class _MotEmbedProjFn(torch.autograd.Function):
         K, Do = desc.out_dim, W.shape[0]
         if W.shape[1] != K:
             raise RuntimeError(f"mot_b200: projection weight is {tuple(W.shape)}, expected [{Do}, {K}]")
-        w16 = W.detach().to(torch.bfloat16).contiguous()      # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
+        w16 = W.detach().to(cdt).contiguous()                  # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
         ctx.ws = None
         if any(ctx.needs_input_grad[4:6]) and n > 0:
             ctx.ws = acquire_workspace(desc, dev)
             embed_plan_async(desc, tok, ctx.ws, dev)
-        A = torch.empty((n, K), dtype=torch.bfloat16, device=dev)
+        A = torch.empty((n, K), dtype=cdt, device=dev)
         embed_forward_out(desc, tok, ids, None, E_tok_c, E_byte_c, None, A)
-        Y = torch.empty((n, Do), dtype=torch.bfloat16, device=dev)
+        Y = torch.empty((n, Do), dtype=cdt, device=dev)
         b32 = bias.detach().float().contiguous() if bias is not None else None
         linear_forward_out(A, w16, Y, b32)
         del A
@@ -483,14 +515,15 @@ class _MotEmbedProjFn(torch.autograd.Function):
         tok, ids, E_tok, E_byte, w16, Y = ctx.saved_tensors
         desc, dev, spec = ctx.desc, ctx.dev, ctx.spec
         n, K, Do = tok.numel(), desc.out_dim, w16.shape[0]
-        g = grad_out.reshape(n, Do).to(torch.bfloat16).contiguous()
+        cdt = Y.dtype
+        g = grad_out.reshape(n, Do).to(cdt).contiguous()
         if spec.out_norm:
             dY = torch.empty_like(Y)
             rmsnorm_backward_out(Y, g, dY, spec.eps)
         else:
             dY = g
         g_bias = dY.float().sum(0) if ctx.has_bias else None
-        A = torch.empty((n, K), dtype=torch.bfloat16, device=dev)
+        A = torch.empty((n, K), dtype=cdt, device=dev)
         embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)       # gathered again, not kept
         dW32 = torch.empty((Do, K), dtype=torch.float32, device=dev)
         dW16 = torch.empty((Do, K), dtype=torch.bfloat16, device=dev) if ctx.w_dtype == torch.bfloat16 else None
@@ -519,8 +552,9 @@ def mot_embed_proj(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Te
                    W: torch.Tensor, spec: MixSpec, *, bpt: int = 16, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Concat + dense projection variants: `norm(F.linear(cat([f(tok), f(bytes)]), W))` (runs/7:226-234, runs/72,
     spt/train_gpt.py:439-443).  spec.tok_norm / byte_norm are the per-input norms, spec.out_norm the norm after the
-    projection, spec.bytes_first the operand order.  Tables bf16; W bf16 (runs) or an fp32 master (spt: cast per call,
-    gradient returned in fp32).  Returns [n_tokens, W.shape[0]] bf16."""
+    projection, spec.bytes_first the operand order.  Tables bf16 with W bf16 (runs) or an fp32 master (spt: cast per
+    call, gradient returned in fp32); or everything fp32 (mathblations: TF32 tensor cores).  Returns
+    [n_tokens, W.shape[0]] in the table dtype."""
     return _MotEmbedProjFn.apply(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias)
 
 

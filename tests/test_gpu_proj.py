@@ -56,16 +56,16 @@ def test_linear_kernels_match_fp32_matmul(n, K, Do):
     assert nerr(dw16, ref) <= TOL_KERNEL
 
 
-def test_linear_refuses_fp32_operands_and_misaligned_dims():
+def test_linear_refuses_fp16_operands_and_misaligned_dims():
     from mot_b200 import ops, _lib as L
     d = dev()
-    x = torch.randn(8, 64, device=d)
+    x = torch.randn(8, 64, device=d).half()
     with pytest.raises(NotImplementedError):
         ops.linear_forward_out(x, x, torch.empty(8, 8, device=d))
     xb = torch.randn(8, 60, device=d).bfloat16()
     with pytest.raises(RuntimeError):
         ops.linear_forward_out(xb, xb, torch.empty(8, 8, dtype=torch.bfloat16, device=d))
-    assert L.lib().mot_linear_fwd(None, None, None, None, 0, 64, 64, 0, None) == L.OK   # empty batch
+    assert L.lib().mot_linear_fwd(None, None, None, None, 0, 64, 64, L.BF16, 0, None) == L.OK   # empty batch
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -174,3 +174,86 @@ def test_spt_module_refuses_unsupported_options():
     for kw in (dict(byte_mixin_method="cross_attn"), dict(use_byte_self_attn=True), dict(add_padded_and_pulled=True)):
         with pytest.raises(NotImplementedError):
             mot_b200.SptByteMixEmbedding(100, 458, 64, 16, 128, 16, **kw)
+
+
+# ------------------------------------------------------------------ fp32 operands on the TF32 tensor-core path (V8)
+TOL_TF32 = 2.0 ** -9   # tf32 keeps 10 mantissa bits; mathblations itself runs F.linear in TF32 (main.py:522)
+
+
+@pytest.mark.parametrize("n,K,Do", [(33, 64, 32), (128, 1280, 256), (11264, 1280, 256), (1000, 328, 72)])
+def test_linear_kernels_tf32_match_fp32_matmul(n, K, Do):
+    from mot_b200 import ops
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(n + K)
+    x = torch.randn(n, K, generator=g, device=d)
+    w = torch.randn(Do, K, generator=g, device=d) / K ** 0.5
+    dy = torch.randn(n, Do, generator=g, device=d)
+    bias = torch.randn(Do, generator=g, device=d)
+    y = torch.empty(n, Do, device=d)
+    ops.linear_forward_out(x, w, y, bias)
+    assert nerr(y, x.double() @ w.double().t() + bias.double()) <= TOL_TF32
+    dx = torch.empty(n, K, device=d)
+    ops.linear_bwd_input_out(dy, w, dx)
+    assert nerr(dx, dy.double() @ w.double()) <= TOL_TF32
+    dw = torch.empty(Do, K, device=d)
+    ops.linear_bwd_weight_out(dy, x, dw)
+    assert nerr(dw, dy.double().t() @ x.double()) <= TOL_TF32
+    with pytest.raises(NotImplementedError):   # mixed operand dtypes are refused, not converted behind the caller's back
+        ops.linear_forward_out(x, w.bfloat16(), y)
+
+
+def test_mathblations_digit_mixin_matches_reference_golden(golden_dir):
+    """DigitMixinConcat (mathblations/model.py:256-268,323-327) on the reference's own inputs / outputs, and the digit
+    expansion of GenerateEquations.tokens_to_digits bit-exact."""
+    import mot_b200
+    g = np.load(os.path.join(golden_dir, "mathblations.npz"))
+    d = dev()
+    dpt, op, eq, pad, _ = (int(v) for v in g["digits_meta"])
+    got = mot_b200.tokens_to_digits(torch.from_numpy(g["digits_tokens"]).to(d), dpt, op, eq, pad)
+    assert np.array_equal(got.cpu().numpy(), g["digits_out"])
+    toks = torch.tensor([0, 7, 10, 99, 105, 9999, op, eq, pad], dtype=torch.int32, device=d)
+    want = O.tokens_to_digits(toks.cpu().tolist(), 4, op, eq, pad)
+    assert np.array_equal(mot_b200.tokens_to_digits(toks, 4, op, eq, pad, out_dtype=torch.int32).cpu().numpy(), want)
+
+    V, Dt = g["mix_wte"].shape
+    Dd = g["mix_dte"].shape[1]
+    dpt_m = g["mix_digits"].shape[1] // g["mix_idx"].shape[1]
+    m = mot_b200.DigitMixinEmbedding(V, Dt, Dd, dpt_m).to(d)
+    with torch.no_grad():
+        m.wte.weight.copy_(torch.from_numpy(g["mix_wte"]))
+        m.dte.weight.copy_(torch.from_numpy(g["mix_dte"]))
+        m.digit_mixin.fc.weight.copy_(torch.from_numpy(g["mix_fc_w"]))
+        m.digit_mixin.fc.bias.copy_(torch.from_numpy(g["mix_fc_b"]))
+    assert sorted(m.state_dict()) == ["digit_mixin.fc.bias", "digit_mixin.fc.weight", "dte.weight", "wte.weight"]
+    out = m(torch.from_numpy(g["mix_idx"]).to(d), torch.from_numpy(g["mix_digits"]).to(d))
+    out.backward(torch.from_numpy(g["mix_gout"]).to(d))
+    assert out.dtype == torch.float32
+    assert nerr(out, torch.from_numpy(g["mix_out"])) <= TOL_TF32
+    assert nerr(m.wte.weight.grad, torch.from_numpy(g["mix_gwte"])) <= TOL_TF32
+    assert nerr(m.dte.weight.grad, torch.from_numpy(g["mix_gdte"])) <= TOL_TF32
+    assert nerr(m.digit_mixin.fc.weight.grad, torch.from_numpy(g["mix_gfc_w"])) <= TOL_TF32
+    assert nerr(m.digit_mixin.fc.bias.grad, torch.from_numpy(g["mix_gfc_b"])) <= 1e-5
+
+
+def test_mathblations_config2_vs_oracle():
+    """BASELINE config 2: B=1024, S=11, dpt 4, vocab 10003, 256/256 -> K = 1280, fp32 (SURVEY 8d cfg 2)."""
+    import mot_b200
+    d = dev()
+    g = torch.Generator().manual_seed(2)
+    B, S, dpt, V, Dt, Dd = 1024, 11, 4, 10003, 256, 256
+    idx = torch.randint(0, 10000, (B, S), generator=g)
+    idx[torch.rand(B, S, generator=g) < 0.2] = 10000          # operator tokens
+    digits = torch.from_numpy(O.tokens_to_digits(idx.reshape(-1).tolist(), dpt, 10000, 10001, 10002)).view(B, S * dpt)
+    m = mot_b200.DigitMixinEmbedding(V, Dt, Dd, dpt)
+    gout = torch.randn(B * S, Dt, generator=g)
+    spec = O.VARIANTS["V8"][0]
+    want_out, want = O.mot_embed_fwd_bwd(spec, idx.reshape(-1).int(), digits.reshape(1, -1), m.wte.weight.detach(), m.dte.weight.detach(),
+                                         gout, bpt=dpt, W=m.digit_mixin.fc.weight.detach(), bias=m.digit_mixin.fc.bias.detach())
+    m = m.to(d)
+    out = m(idx.to(d), digits.to(d))
+    out.backward(gout.to(d).view_as(out))
+    assert nerr(out.view(B * S, Dt), want_out) <= TOL_TF32
+    assert nerr(m.wte.weight.grad, want["E_tok"]) <= TOL_TF32
+    assert nerr(m.dte.weight.grad, want["E_byte"]) <= TOL_TF32
+    assert nerr(m.digit_mixin.fc.weight.grad, want["W"]) <= TOL_TF32
+    assert nerr(m.digit_mixin.fc.bias.grad, want["bias"]) <= 1e-4

@@ -14,14 +14,14 @@ for (n, K, Do) in [(128, 64, 256), (256, 128, 256), (1000, 1024, 1024), (4096, 2
     w = (torch.randn(Do, K, generator=g, device=d) / K ** 0.5).bfloat16()
     dy = torch.randn(n, Do, generator=g, device=d).bfloat16()
     y = torch.empty(n, Do, dtype=torch.bfloat16, device=d)
-    rc = lib.mot_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), n, K, Do, 0, st()); torch.cuda.synchronize()
+    rc = lib.mot_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), n, K, Do, 0, 0, st()); torch.cuda.synchronize()
     ref = x.float() @ w.float().t()
     print(f"n={n} K={K} Do={Do} fwd rc={rc} err={rel(y, ref):.2e}", end=" | ")
     dx = torch.empty(n, K, dtype=torch.bfloat16, device=d)
-    rc = lib.mot_linear_bwd_input(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, K, Do, st()); torch.cuda.synchronize()
+    rc = lib.mot_linear_bwd_input(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, K, Do, 0, None, 0, st()); torch.cuda.synchronize()
     print(f"dX rc={rc} err={rel(dx, dy.float() @ w.float()):.2e}", end=" | ")
     dw = torch.empty(Do, K, dtype=torch.float32, device=d); dwb = torch.empty(Do, K, dtype=torch.bfloat16, device=d)
-    rc = lib.mot_linear_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), dwb.data_ptr(), n, K, Do, st()); torch.cuda.synchronize()
+    rc = lib.mot_linear_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), dwb.data_ptr(), n, K, Do, 0, None, 0, st()); torch.cuda.synchronize()
     refw = dy.float().t() @ x.float()
     print(f"dW rc={rc} err={rel(dw, refw):.2e} bf16 {rel(dwb, refw):.2e}")
 # timing at the runs/7 shape
@@ -34,6 +34,6 @@ def t(fn, reps=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 fl = 2.0 * n * K * Do
-print("fwd  %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), n, K, Do, 0, st()))), fl / tf / 1e9, t(lambda: torch.matmul(x, w.t()))))
-print("dX   %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_bwd_input(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, K, Do, st()))), fl / tf / 1e9, t(lambda: torch.matmul(dy, w))))
-print("dW   %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), dwb.data_ptr(), n, K, Do, st()))), fl / tf / 1e9, t(lambda: torch.matmul(dy.t(), x))))
+print("fwd  %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), n, K, Do, 0, 0, st()))), fl / tf / 1e9, t(lambda: torch.matmul(x, w.t()))))
+print("dX   %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_bwd_input(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), n, K, Do, 0, None, 0, st()))), fl / tf / 1e9, t(lambda: torch.matmul(dy, w))))
+print("dW   %.3f ms %.0f TFLOP/s | torch %.3f ms" % ((tf := t(lambda: lib.mot_linear_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), dwb.data_ptr(), n, K, Do, 0, None, 0, st()))), fl / tf / 1e9, t(lambda: torch.matmul(dy.t(), x))))
