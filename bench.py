@@ -50,6 +50,9 @@ WORKLOADS = {
     # scaled-pre-train default (256/48 -> 1024, K = 1024, B=64 x S=1024 per GPU, spt/train_gpt.py:822)
     "mot-proj-runs7-64k": dict(variant="V1", N=65536, Dt=1024, bd=64, bpt=16, Do=1024, dtype="bf16"),
     "mot-proj-spt-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16"),
+    # BASELINE.json configs[1]: mathblations digit mixin (mathblations/model.py:256-268): B=1024, S=11, dpt 4,
+    # vocab 10003, 256/256 -> K = 1280 -> 256, fp32 parameters, TF32 matmul; launch-latency bound
+    "mathblations-concat": dict(variant="V8", N=1024 * 11, Dt=256, bd=256, bpt=4, Do=256, dtype="f32"),
 }
 DEFAULT_WORKLOAD = "mot-sum-124M-48k"
 
@@ -585,11 +588,79 @@ def run_proj(args):
         dist.destroy_process_group()
 
 
+def run_mathblations(args):
+    """Config 2: the whole module step (digits expansion + fused gather + TF32 projection, forward and backward)."""
+    import mot_b200
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("mathblations-concat is a 1-GPU configuration (BASELINE.json configs[1])")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    w = workload_config(args)
+    B, S, dpt, V = 1024, 11, w["bpt"], 10003
+    g = torch.Generator().manual_seed(12345)
+    idx_host = torch.randint(0, 10000, (B, S), generator=g)
+    idx_host[torch.rand(B, S, generator=g) < 0.2] = 10000
+    idx_host = idx_host.pin_memory()
+    m = mot_b200.DigitMixinEmbedding(V, w["Dt"], w["bd"], dpt).to(dev)
+    gout = torch.randn(B, S, w["Do"], device=dev)
+    res_host = torch.empty(14, w["bd"]).pin_memory()
+    idx = idx_host.to(dev)
+
+    def step(e2e=False):
+        for p_ in m.parameters():
+            p_.grad = None
+        t = idx_host.to(dev, non_blocking=True) if e2e else idx
+        digits = mot_b200.tokens_to_digits(t, dpt, 10000, 10001, 10002).view(B, S * dpt)
+        m(t, digits).backward(gout)
+        if e2e:
+            res_host.copy_(m.dte.weight.grad, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+    mot_b200.reset_launch_count()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    launches = mot_b200.launch_count()
+    ms_step = e0.elapsed_time(e1) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step(e2e=True)
+    t_e = (time.perf_counter() - t0) / K
+    clocks = sampler.stop()
+    N, Kd, Do = w["N"], w["Dt"] + dpt * w["bd"], w["Do"]
+    peak, peak_src = measured_tensor_peak()
+    flops = 6.0 * N * Kd * Do
+    line = {"metric": "byte-mix embedding fwd+bwd tokens/sec", "value": N / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": 1,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tf32 tensor cores)", "data": "synthetic",
+            "config": {"workload": w["name"], "variant": "V8 digits concat + linear with bias (mathblations/model.py:256-268)",
+                       "batch": B, "seq": S, "digits_per_token": dpt, "n_embd_tok": w["Dt"], "n_embd_digit": w["bd"],
+                       "l2": "working set fits L2: launch-latency bound configuration, reported as us/step", "parallelism": "dp1"},
+            "us_per_step": ms_step * 1e3,
+            "roofline": {"bound": "tensor", "kernel": "mot_gemm_kernel<float> (fwd + dX + dW)", "achieved": flops / (ms_step * 1e-3) / 1e12,
+                         "peak": peak, "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / peak, "traffic": None,
+                         "peak_source": peak_src + "; whole-step time: the step is launch-latency bound, not tensor bound"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": N / t_e, "unit": "tokens/s", "h2d_bytes_per_step": idx_host.numel() * 8,
+                    "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": t_e * 1e3,
+                    "api": "mot_b200.tokens_to_digits + DigitMixinEmbedding.forward + autograd backward", "steps": K}}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
     elif WORKLOADS[a.workload]["variant"] == "V1":
         run_proj(a)
+    elif WORKLOADS[a.workload]["variant"] == "V8":
+        run_mathblations(a)
     else:
         run_ours(a)
