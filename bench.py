@@ -283,9 +283,13 @@ def run_ours(args):
     gout = torch.randn(N, Do, generator=gd, device=dev).to(dt)
     lam = torch.tensor([0.5, 0.5], device=dev) if w["variant"] in ("V3c", "V3d") else None
     out = torch.empty(N, Do, dtype=dt, device=dev)
+    # what F.rms_norm's autograd node keeps: the forward result and rstd (read by the saved-output backward of the
+    # MoT-sum variant; the other variants rebuild the mixed row and ignore them)
+    rstd = torch.empty(N, dtype=torch.float32, device=dev) if (w["variant"] == "V3" and not os.environ.get("MOT_NO_SAVED_BWD")) else None
     # one flat gradient bucket [gE_tok | gE_byte] the backward writes into -> a single NCCL all-reduce
     from mot_b200 import dp
-    bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False)])
+    bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False)],
+                           symmetric=(world > 1 and not os.environ.get("MOT_DP_NCCL")))
     gE_tok, gE_byte = bucket.views()
     g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
@@ -296,10 +300,10 @@ def run_ours(args):
         # the same call sequence as mot_b200.mot_embed + autograd: the backward plan (counting sort of the token ids)
         # is launched on a side stream beside the forward kernel, the backward waits for it
         ops.embed_plan_async(desc, tok, ws, dev)
-        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out)
+        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out, rstd=rstd)
         ops.embed_plan_join(ws, dev)
         ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf,
-                               plan_ready=True, ws_clean=True)
+                               plan_ready=True, ws_clean=True, out_saved=out if rstd is not None else None, rstd=rstd)
         ws.clean = True
         if world > 1:
             bucket.all_reduce_avg()
@@ -392,7 +396,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        dom_bytes, dom_ms, dom = (A_bwd, bwd_ms, "mot_bwd_kernel") if bwd_ms >= fwd_ms else (A_fwd, fwd_ms, "mot_fwd_kernel")
+        dom_bytes, dom_ms, dom = (A_bwd, bwd_ms, "mot_bwd_sum_kernel" if rstd is not None else "mot_bwd_kernel") if bwd_ms >= fwd_ms else (A_fwd, fwd_ms, "mot_fwd_kernel")
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         line = {
             "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
@@ -402,7 +406,9 @@ def run_ours(args):
                        "byte_dim": bd, "bytes_per_token": bpt, "out_dim": Do, "token_dist": args.dist,
                        "byte_ids": "uniform randint(0,458), given as a tensor (runs/7:635 layout)",
                        "l2": f"working set {(2 * V_TOK * Dt * esz + 2 * N * Do * esz) / 1e6:.0f} MB > 126 MB L2, no flush",
-                       "parallelism": f"dp{world}" + (", one flat-bucket NCCL all-reduce(AVG) per step" if world > 1 else "")},
+                       "parallelism": f"dp{world}" + ((", one flat-bucket all-reduce(AVG) per step: " +
+                                                       ("own NVLS kernel over multicast symmetric memory" if bucket._symm is not None else "NCCL"))
+                                                      if world > 1 else "")},
             "tokens_per_sec_per_gpu": value / world,
             "kernel_ms": {"fwd": fwd_ms, "bwd_main": bwd_ms},
             "step_hbm_gbs": (A_fwd + A_bwd) / (ms_step * 1e-3) / 1e9,

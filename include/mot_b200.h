@@ -135,6 +135,13 @@ int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_t ws_bytes,
 int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                   const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream);
 
+/* The same forward that also keeps rstd_out[n_tokens] (fp32, device): the reciprocal rms of every mixed row, i.e.
+ * what F.rms_norm's autograd node saves (spt/train_gpt.py:172-173).  Written when MOT_F_OUT_NORM is set; NULL = not
+ * kept.  Together with `out` it lets mot_embed_bwd_saved skip rebuilding the mixed row. */
+int mot_embed_fwd_save(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                       const void* E_tok, const void* E_byte, const float* lam, void* out, float* rstd_out,
+                       void* stream);
+
 /* Sort plan for the backward (token ids only; reusable by every table gathered with `tok`). */
 int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
                    void* stream);
@@ -156,6 +163,25 @@ int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
                   const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                   void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                   int32_t ws_flags, void* stream);
+
+/* mot_embed_bwd with the forward's result kept (out_saved = the `out` of mot_embed_fwd_save, rstd_saved = its
+ * rstd_out; both NULL = plain mot_embed_bwd).  For the MoT-sum variant (MOT_ADD + MOT_F_OUT_NORM only, runs/71) the
+ * backward then reads two rows per occurrence (grad_out and out, same position) instead of the token row plus bpt byte
+ * rows: dz = rstd*g - out*(rstd*mean(g.out)).  Other variants ignore the two pointers.  Same results within the
+ * rounding of `out` (bf16: one extra 2^-9 relative rounding inside the second term). */
+int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                        const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                        const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte, float* g_lam,
+                        void* workspace, size_t ws_bytes, int32_t ws_flags, void* stream);
+
+/* ---- data-parallel exchange: average the gradient bucket across ranks through NVLink / NVSwitch (NVLS) -----------
+ * Replaces the per-parameter dist.all_reduce(param.grad, AVG) of spt/train_gpt.py:1320-1321 and runs/7:697-700 for the
+ * tensors this path owns.  `multicast_ptr` is the multicast mapping of the same symmetric-memory buffer on every rank
+ * (n_bytes, multiple of 16); `signal_pads_dev` a device array of `world` pointers to the ranks' zero-initialised
+ * uint32 signal pads (>= 128*world slots); `epoch` a call counter that grows by one per call on every rank (start at
+ * 1).  In place, result on every rank; ordered on `stream` after the local backward. */
+int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
+                         int32_t dtype, uint32_t epoch, void* stream);
 
 /* ---- byte pull across tokens ------------------------------------------------------------------------------
  * Replaces pull_from_left / pull_from_right (spt/data_creation.py:179-305 / :71-176, runs/7:351-428).

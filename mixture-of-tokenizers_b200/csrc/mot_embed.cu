@@ -1,5 +1,7 @@
 // Host side of the fused byte-mix embedding: validation, workspace layout, plan, C ABI.
-#include "mot_embed_kernels.cuh"
+#include <algorithm>
+
+#include "mot_embed_bwd_sum.cuh"
 
 namespace mot {
 
@@ -96,6 +98,17 @@ __global__ void mot_lam_store_kernel(float* __restrict__ acc, float* __restrict_
 // ======================================================================================
 // Host side
 // ======================================================================================
+// Stream chunk size: one chunk per backward warp of a full B200 (148 SMs x warps per CTA), so that every warp walks
+// the same number of stream entries; chunks longer than one 32-entry batch are whole batches.  (A constant, not the
+// current device's SM count: the workspace layout must not depend on the device.)
+static int stream_chunk(long long n_tokens, int warps_per_cta) {
+  const long long warps = 148LL * warps_per_cta;
+  long long R = (n_tokens + warps - 1) / warps;
+  if (R < 1) R = 1;
+  if (R > 32) R = (R + 31) / 32 * 32;
+  return (int)R;
+}
+
 static int validate(const MotDesc* d) {
   if (!d) return MOT_ERR_BAD_ARG;
   if (d->abi_version != MOT_B200_ABI_VERSION) return MOT_ERR_BAD_ARG;
@@ -147,14 +160,7 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.io_ld = d->out_dim;
   p.io_col = 0;
   p.eps = d->eps;
-  // stream chunk size: one chunk per backward warp of a full B200 (148 SMs x kBwdThreads/32 warps), so that every
-  // warp walks the same number of stream entries; chunks longer than one 32-entry batch are whole batches.
-  // (A constant, not the current device's SM count: the workspace layout must not depend on the device.)
-  const long long warps = 148LL * (kBwdThreads / 32);
-  long long R = (d->n_tokens + warps - 1) / warps;
-  if (R < 1) R = 1;
-  if (R > 32) R = (R + 31) / 32 * 32;
-  p.R = (int)R;
+  p.R = stream_chunk(d->n_tokens, kBwdThreads / 32);  // the saved-output kernel re-chunks for its own CTA size
   p.n_rep = kByteRep;
   p.stages = 4;
   p.tab_smem = 1;
@@ -191,7 +197,9 @@ struct WsLayout {
 static WsLayout ws_layout(const EmbedParams& p) {
   WsLayout w{};
   const long long V = p.V > 0 ? p.V : 1, N = p.N > 0 ? p.N : 1;
-  const long long n_stream_chunks = (N + p.R - 1) / p.R;
+  // one fp32 slot per stream chunk, sized for the finer of the two chunkings (recompute / saved-output kernel)
+  const int r_min = std::min(p.R, stream_chunk(N, kSumThreads / 32));
+  const long long n_stream_chunks = (N + r_min - 1) / r_min;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -246,6 +254,12 @@ extern "C" size_t mot_embed_workspace_bytes(const MotDesc* d) {
 
 extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream) {
+  return mot_embed_fwd_save(d, tok, byte_ids, ttb, E_tok, E_byte, lam, out, nullptr, stream);
+}
+
+extern "C" int mot_embed_fwd_save(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                  const void* E_tok, const void* E_byte, const float* lam, void* out, float* rstd_out,
+                                  void* stream) {
   if (int rc = validate(d)) return rc;
   if (d->n_tokens == 0) return MOT_OK;  // empty batch: nothing to write (empty tensors have null pointers)
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
@@ -269,6 +283,7 @@ extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* b
   EmbedParams p;
   fill_params(d, p);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam; p.out = out;
+  p.rstd_out = (d->flags & MOT_F_OUT_NORM) ? rstd_out : nullptr;
   return d->dtype == MOT_BF16 ? dispatch_fwd_bf16(p, s) : dispatch_fwd_f32(p, s);
 }
 
@@ -325,6 +340,14 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
                              const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                              void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                              int32_t ws_flags, void* stream) {
+  return mot_embed_bwd_saved(d, tok, byte_ids, ttb, E_tok, E_byte, lam, grad_out, nullptr, nullptr, gE_tok, gE_byte, g_lam,
+                             workspace, ws_bytes, ws_flags, stream);
+}
+
+extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                   const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                                   const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte,
+                                   float* g_lam, void* workspace, size_t ws_bytes, int32_t ws_flags, void* stream) {
   const bool plan_ready = (ws_flags & MOT_WS_PLAN_READY) != 0, ws_clean = (ws_flags & MOT_WS_CLEAN) != 0;
   if (int rc = validate(d)) return rc;
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
@@ -378,7 +401,23 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
       if ((rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(*q, s) : dispatch_bwd_f32(*q, s))) return rc;
     }
   } else {
-    rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
+    // the MoT-sum variant with the forward result kept: the saved-output kernel (mot_embed_bwd_sum.cuh); every other
+    // case, or no instantiation for this width, recomputes the mixed row
+    static const bool no_saved = getenv("MOT_NO_SAVED_BWD") != nullptr;  // debug knob (A/B timing)
+    rc = -1;
+    // Beyond ~4 positions per vocabulary row the recompute kernel wins: its token rows are re-read from L2 (the
+    // sorted stream visits a row's occurrences back to back) while the saved rows are all distinct HBM reads
+    // (768 = 16 x 48 bf16, V = 50257: 131K tokens 118 vs 132 us, 262K 225 vs 218 us, 1M 921 vs 795 us; gpurun_out/run4.log).
+    if (out_saved && rstd_saved && !no_saved && p.N <= 4LL * p.V) {
+      if (!aligned16(out_saved)) return MOT_ERR_MISALIGNED;
+      p.out_saved = out_saved;
+      p.rstd = rstd_saved;
+      const int r_default = p.R;
+      p.R = stream_chunk(p.N, kSumThreads / 32);  // the finalize pass below reads the same p.R
+      rc = d->dtype == MOT_BF16 ? dispatch_bwd_sum_bf16(p, s) : dispatch_bwd_sum_f32(p, s);
+      if (rc < 0) p.R = r_default;
+    }
+    if (rc < 0) rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
   }
   if (rc) return rc;
   int sms = 0, optin = 0;

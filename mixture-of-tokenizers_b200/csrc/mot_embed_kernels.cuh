@@ -31,7 +31,10 @@ constexpr int kFwdThreads = 768;
 #define MOT_BWD_THREADS 384
 #endif
 constexpr int kBwdThreads = MOT_BWD_THREADS;
-constexpr int kByteRep = 16;  // replicas of the fp32 byte-grad accumulator (spreads hot byte ids over L2 atomic units)
+#ifndef MOT_BYTE_REP
+#define MOT_BYTE_REP 16
+#endif
+constexpr int kByteRep = MOT_BYTE_REP;  // replicas of the fp32 byte-grad accumulator (spreads hot byte ids over L2 atomic units)
 
 struct EmbedParams {
   const int32_t* tok;
@@ -41,8 +44,11 @@ struct EmbedParams {
   const void* E_byte;
   const float* lam;
   void* out;
+  float* rstd_out;  // optional [N]: reciprocal rms of every mixed row (out_norm), kept for the saved-output backward
   // backward
   const void* gout;
+  const void* out_saved;  // optional: the forward result and its rstd (mot_embed_bwd_saved)
+  const float* rstd;
   void* gE_tok;
   void* gE_byte;
   float* g_lam;
@@ -145,7 +151,7 @@ __device__ __forceinline__ int clamp_id(const EmbedParams& p, int id) { return c
 // Per-lane view of the byte-id source, set up once: one multiply-add + load per position.
 struct IdSrc {
   const char* base;      // address of (position 0, slot = lane) for id tensors
-  long long pos_stride;  // bytes between consecutive positions
+  unsigned pos_stride;   // bytes between consecutive positions (<= 8 * 32)
   int kind;              // 0: int32 tensor, 1: int64 tensor, 2: derived from the ttb table
 };
 __device__ __forceinline__ IdSrc make_id_src(const EmbedParams& p, int slot) {
@@ -154,12 +160,12 @@ __device__ __forceinline__ IdSrc make_id_src(const EmbedParams& p, int slot) {
   s.kind = (p.flags & MOT_F_IDS_FROM_TTB) ? 2 : ((p.flags & MOT_F_IDS_I64) ? 1 : 0);
   const bool sm = (p.flags & MOT_F_SLOT_MAJOR) != 0;
   s.base = reinterpret_cast<const char*>(p.ids) + (sm ? (long long)slot * p.N : (long long)slot) * esz;
-  s.pos_stride = (sm ? 1LL : (long long)p.bpt) * esz;
+  s.pos_stride = (unsigned)((sm ? 1 : p.bpt) * esz);
   return s;
 }
 __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s, int pos, int slot) {
   if (s.kind == 2) return fetch_id(p, pos, slot);
-  const char* a = s.base + (long long)pos * s.pos_stride;
+  const char* a = s.base + (unsigned long long)(unsigned)pos * s.pos_stride;  // one 32 x 32 -> 64 multiply-add
   return s.kind == 1 ? (int)__ldg(reinterpret_cast<const long long*>(a)) : __ldg(reinterpret_cast<const int*>(a));
 }
 
@@ -202,9 +208,11 @@ __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& 
 }
 
 // Stage E_byte into shared memory (bulk async copies of <= 32 KB) and compute the per-row rms scale
-// of byte_norm: rs[r] = rsqrt(mean(row^2) + eps), or 1.  Ends with __syncthreads().
+// of byte_norm: rs[r] = rsqrt(mean(row^2) + eps), or 1.  Ends with __syncthreads().  need_rs == false (a variant that
+// never scales byte rows: the MoT-sum fast path) skips the scale pass: every thread has waited on the copy barrier
+// itself, which is all the table reads need.
 template <typename T>
-__device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar) {
+__device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar, bool need_rs) {
   if (p.tab_smem) {
     const uint32_t bytes = (uint32_t)p.Vb * p.bd * sizeof(T);
     if (threadIdx.x == 0) {
@@ -217,6 +225,7 @@ __device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64
     }
     mbar_wait(bar, 0);
   }
+  if (!need_rs) return;
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = lane_id();
   const bool bn = (p.flags & MOT_F_BYTE_NORM) != 0;
   for (int r = warp; r < p.Vb; r += nw) {
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     }
     if (D < n_i) tok_ahead = __ldg(p.tok + gw + D * stride);  // raw; clamped where it is used
   }
-  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar);
+  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar, C::byte_scale(p));
 
   ChunkMap cm[CPL];
 #pragma unroll
@@ -421,6 +430,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     if (out_norm) {
       ss = warp_sum(ss);  // every lane has consumed its shared-memory reads here: the stage can be refilled
       oscale = rsqrtf(ss * inv_Do + p.eps);
+      if (p.rstd_out != nullptr && lane == 0) p.rstd_out[pos] = oscale;
     } else {
       __syncwarp();
     }
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   while (issued < D && try_issue()) {
   }
 
-  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar);  // ring prologue already in flight
+  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar, C::byte_scale(p));  // ring prologue already in flight
 
   ChunkMap cm[CPL];
 #pragma unroll
@@ -968,23 +978,33 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (c < nc) {
           const float* src = p.byte_acc + (size_t)r * p.bd + c * kChunk;
-          float4 x[kByteRep], y[kByteRep];
-#pragma unroll
-          for (int rep = 0; rep < kByteRep; ++rep) {
-            x[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride);
-            y[rep] = *reinterpret_cast<const float4*>(src + rep * rep_stride + 4);
-          }
-          // leave the accumulators zeroed for the next call (the workspace cleans itself, see MOT_WS_CLEAN)
+          // groups of 8 replicas: 16 independent 16-byte loads in flight, zeroed again for the next call (the
+          // workspace cleans itself, see MOT_WS_CLEAN), then summed
           float* dst = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+#pragma unroll 1
+          for (int r0 = 0; r0 < kByteRep; r0 += 8) {
+            float4 x[8], y[8];
 #pragma unroll
-          for (int rep = 0; rep < kByteRep; ++rep) {
-            *reinterpret_cast<float4*>(dst + rep * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(dst + rep * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+            for (int rep = 0; rep < 8; ++rep) {
+              if (r0 + rep < kByteRep) {
+                x[rep] = *reinterpret_cast<const float4*>(src + (r0 + rep) * rep_stride);
+                y[rep] = *reinterpret_cast<const float4*>(src + (r0 + rep) * rep_stride + 4);
+              }
+            }
 #pragma unroll
-          for (int rep = 0; rep < kByteRep; ++rep) {
-            a[0] += x[rep].x; a[1] += x[rep].y; a[2] += x[rep].z; a[3] += x[rep].w;
-            a[4] += y[rep].x; a[5] += y[rep].y; a[6] += y[rep].z; a[7] += y[rep].w;
+            for (int rep = 0; rep < 8; ++rep) {
+              if (r0 + rep < kByteRep) {
+                *reinterpret_cast<float4*>(dst + (r0 + rep) * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(dst + (r0 + rep) * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int rep = 0; rep < 8; ++rep) {
+              if (r0 + rep < kByteRep) {
+                a[0] += x[rep].x; a[1] += x[rep].y; a[2] += x[rep].z; a[3] += x[rep].w;
+                a[4] += y[rep].x; a[5] += y[rep].y; a[6] += y[rep].z; a[7] += y[rep].w;
+              }
+            }
           }
           if (bn) Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
         }
@@ -1088,6 +1108,8 @@ int dispatch_fwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
+int dispatch_bwd_sum_bf16(const EmbedParams& p, cudaStream_t s);  // saved-output MoT-sum kernel; -1: not applicable
+int dispatch_bwd_sum_f32(const EmbedParams& p, cudaStream_t s);
 int launch_finalize_bf16(const EmbedParams& p, int blocks, cudaStream_t s);
 int launch_finalize_f32(const EmbedParams& p, int blocks, cudaStream_t s);
 

@@ -8,6 +8,8 @@ backward kernels write into directly, so the exchange is a single NCCL all-reduc
 copy.  Pure torch.distributed host logic: works with any backend (the CPU tests run it over gloo)."""
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Iterable, List, Optional
 
 import torch
@@ -33,7 +35,10 @@ class GradBucket:
     overwrites every row, so no zeroing is needed), `attach()` points `param.grad` at them, `all_reduce_avg()`
     averages the whole bucket across ranks in one collective."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric: bool = False,
+                 group=None):
+        """symmetric=True (CUDA, initialised NCCL group): allocate the bucket in symmetric memory with a multicast
+        mapping so that all_reduce_avg() runs the library's own NVLS kernel (mot_dp_allreduce_avg) instead of NCCL."""
         self.params: List[torch.nn.Parameter] = list(params)
         if not self.params:
             raise ValueError("GradBucket needs at least one parameter")
@@ -47,7 +52,30 @@ class GradBucket:
                 raise ValueError("GradBucket: parameters on different devices")
             self.offsets.append(n)
             n += (p.numel() + align - 1) // align * align
-        self.flat = torch.zeros(n, dtype=self.dtype, device=dev)
+        self._symm = None
+        self._epoch = 0
+        n = (n + align - 1) // align * align
+        self.flat = None
+        if symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() \
+                and not os.environ.get("MOT_DP_NCCL"):
+            # Symmetric memory + multicast need NVSwitch and a driver with fabric support; where either is missing
+            # the bucket is ordinary device memory and the exchange is NCCL's all-reduce (a library collective on
+            # the same data, not a different code path for the kernels).
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                flat = symm_mem.empty(n, dtype=self.dtype, device=dev)
+                flat.zero_()
+                hdl = symm_mem.rendezvous(flat, grp)
+                self.flat = flat
+                if hdl.multicast_ptr != 0:       # NVSwitch multicast (NVLS) available
+                    self._symm = hdl
+            except Exception as e:  # noqa: BLE001 - any allocator / rendezvous failure means "no NVLS here"
+                warnings.warn(f"GradBucket: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL")
+                self.flat = None
+                self._symm = None
+        if self.flat is None:
+            self.flat = torch.zeros(n, dtype=self.dtype, device=dev)
         self._views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
 
     def views(self) -> List[torch.Tensor]:
@@ -74,6 +102,18 @@ class GradBucket:
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world = dist.get_world_size(group)
+        if self._symm is not None and group is None and self.dtype in (torch.bfloat16, torch.float32):
+            # one kernel per rank over the multicast mapping: reduce in the switch, average, multicast back
+            from . import _lib as L
+            h = self._symm
+            self._epoch += 1
+            dev = self.flat.device
+            rc = L.lib().mot_dp_allreduce_avg(h.multicast_ptr, h.signal_pad_ptrs_dev, h.rank, h.world_size,
+                                              self.flat.numel() * self.flat.element_size(),
+                                              L.BF16 if self.dtype == torch.bfloat16 else L.F32, self._epoch,
+                                              torch.cuda.current_stream(dev).cuda_stream)
+            L.check(rc, "mot_dp_allreduce_avg")
+            return None
         if dist.get_backend(group) == "nccl":
             return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)

@@ -180,12 +180,18 @@ def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Opt
                      Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps)
 
 
-def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None) -> None:
-    """mot_embed_fwd on caller-allocated tensors (no allocation, no sync; CUDA-graph capturable)."""
+def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None,
+                      rstd: Optional[torch.Tensor] = None) -> None:
+    """mot_embed_fwd on caller-allocated tensors (no allocation, no sync; CUDA-graph capturable).  `rstd` (fp32
+    [n_tokens]) additionally keeps the reciprocal rms of every mixed row for the saved-output backward."""
     dev = out.device
     with _on_device(dev):
-        rc = L.lib().mot_embed_fwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
-                                   _ptr(out), _stream(dev) if stream is None else stream)
+        if rstd is None:
+            rc = L.lib().mot_embed_fwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                       _ptr(out), _stream(dev) if stream is None else stream)
+        else:
+            rc = L.lib().mot_embed_fwd_save(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                            _ptr(out), _ptr(rstd), _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_fwd")
 
 
@@ -209,15 +215,23 @@ def embed_plan(desc: L.MotDesc, tok, ws, ws_clean: bool = False) -> None:
 
 
 def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
-                       plan_ready: bool = False, ws_clean: bool = False, stream: Optional[int] = None) -> None:
+                       plan_ready: bool = False, ws_clean: bool = False, stream: Optional[int] = None,
+                       out_saved: Optional[torch.Tensor] = None, rstd: Optional[torch.Tensor] = None) -> None:
     """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten.  `ws_clean`: the caller
-    vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward)."""
+    vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward).
+    `out_saved` + `rstd` (what embed_forward_out(..., rstd=) produced): mot_embed_bwd_saved."""
     dev = grad_out.device
     flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0)
     with _on_device(dev):
-        rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
-                                   _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
-                                   flags, _stream(dev) if stream is None else stream)
+        if out_saved is None or rstd is None:
+            rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                       _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
+                                       flags, _stream(dev) if stream is None else stream)
+        else:
+            rc = L.lib().mot_embed_bwd_saved(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                             _ptr(grad_out), _ptr(out_saved), _ptr(rstd), _ptr(gE_tok), _ptr(gE_byte),
+                                             _ptr(g_lam), _ptr(ws), ws.numel(), flags,
+                                             _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_bwd")
 
 
@@ -332,17 +346,23 @@ class _MotEmbedFn(torch.autograd.Function):
         if needs_grad and tok is not None and n > 0:
             ctx.ws = acquire_workspace(desc, dev)
             embed_plan_async(desc, tok, ctx.ws, dev, st)
-        embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st)
+        # MoT-sum (runs/71): keep what rms_norm's autograd node keeps (its result and rstd); the backward then reads two
+        # rows per occurrence instead of rebuilding the mixed row (mot_embed_bwd_saved)
+        keep = needs_grad and n > 0 and spec.combine == "add" and spec.out_norm and lam is None \
+            and not (spec.tok_norm or spec.byte_norm)
+        rstd = torch.empty(n, dtype=torch.float32, device=dev) if keep else None
+        embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st, rstd=rstd)
         ctx.desc, ctx.dev = desc, dev
-        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)])
-        ctx.present = [t is not None for t in (tok, ids, ttb, E_tok_c, E_byte_c, lam_c)]
+        saved = (tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out if keep else None, rstd)
+        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in saved])
+        ctx.present = [t is not None for t in saved]
         ctx.lam_dtype = lam.dtype if lam is not None else None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         saved = [t if ok else None for t, ok in zip(ctx.saved_tensors, ctx.present)]
-        tok, ids, ttb, E_tok, E_byte, lam = saved
+        tok, ids, ttb, E_tok, E_byte, lam, out_saved, rstd = saved
         desc, dev = ctx.desc, ctx.dev
         g = grad_out.contiguous()
         if g.dtype != (E_tok if E_tok is not None else E_byte).dtype:
@@ -368,7 +388,7 @@ class _MotEmbedFn(torch.autograd.Function):
         else:
             clean, ws.clean = ws.clean, False
         embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
-                           plan_ready=planned, ws_clean=clean, stream=st)
+                           plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd)
         ws.clean = True           # every completed backward leaves the head of the workspace zeroed
         ctx.ws = None
         release_workspace(ws)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_has_no_torch_dependency():
     out = os.popen(f"ldd {L.LIB_PATH}").read()
-    assert "torch" not in out and "c10" not in out
+    assert "libtorch" not in out and "libc10" not in out, out
 
 
 def test_strerror_and_codes():

@@ -248,6 +248,58 @@ def test_full_size_properties():
     assert nerr(Eb.grad, want_b) <= 2.0 ** -8
 
 
+@pytest.mark.parametrize("dtype,Dt,bd,bpt,N,V,zipf", [
+    (torch.float32, 512, 64, 8, 333, 200, False),
+    (torch.float32, 768, 48, 16, 5000, 1500, True),       # hot rows straddle stream chunks -> slot + finalize path
+    (torch.float32, 1024, 32, 32, 2049, 50257, False),    # mostly single-occurrence rows, many empty rows
+    (torch.bfloat16, 768, 48, 16, 70001, 3000, True),     # R = 64: two batches per stream chunk, ragged tail
+    (torch.bfloat16, 1024, 64, 16, 4097, 900, False),
+    (torch.bfloat16, 512, 64, 8, 1, 10, False),
+])
+def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V, zipf):
+    """mot_embed_bwd_saved (reads grad_out + the kept forward result, mot_embed_bwd_sum.cuh) against mot_embed_bwd
+    (rebuilds the mixed row) and against the oracle, through the C ABI on caller-allocated tensors."""
+    import mot_b200
+    from mot_b200 import ops
+    d = dev()
+    g = torch.Generator().manual_seed(11)
+    toks = ((torch.rand(N, generator=g) ** 4 * V).long().clamp_(0, V - 1).int() if zipf
+            else torch.randint(0, V, (N,), generator=g, dtype=torch.int32))
+    ids = torch.randint(0, 458, (bpt, N), generator=g, dtype=torch.int32)       # slot-major like runs/71:479
+    E_tok = torch.randn(V, Dt, generator=g).to(dtype)
+    E_byte = torch.randn(458, bd, generator=g).to(dtype)
+    gout = torch.randn(N, Dt, generator=g).to(dtype)
+    want_out, want = O.mot_embed_fwd_bwd(O.VARIANTS["V3"][0], toks, ids, E_tok, E_byte, gout, bpt=bpt, slot_major=True)
+    spec = mot_b200.MixSpec(combine="add", slot_major=True)
+    tk, idd, Et, Eb, go = toks.to(d), ids.to(d), E_tok.to(d), E_byte.to(d), gout.to(d)
+    desc = ops.make_desc(spec, N, Et, Eb, bpt, ids=idd, ttb=None, has_lam=False)
+    out = torch.empty(N, Dt, dtype=dtype, device=d)
+    rstd = torch.full((N,), float("nan"), dtype=torch.float32, device=d)
+    ops.embed_forward_out(desc, tk, idd, None, Et, Eb, None, out, rstd=rstd)
+    z = E_tok.double()[toks.long()] + E_byte.double()[ids.long().t()].reshape(N, -1)
+    want_rstd = torch.rsqrt(z.pow(2).mean(-1) + mot_b200.FP32_EPS)
+    assert nerr(rstd, want_rstd) <= 1e-5
+    ws = torch.empty(ops.embed_workspace_bytes(desc), dtype=torch.uint8, device=d)
+    res = {}
+    for name, kw in (("saved", dict(out_saved=out, rstd=rstd)), ("recompute", {})):
+        for rep in range(2):   # twice on the same workspace: the first call leaves it clean for the second
+            gt = torch.full_like(Et, float("nan"))
+            gb = torch.full_like(Eb, float("nan"))
+            ops.embed_backward_out(desc, tk, idd, None, Et, Eb, None, go, gt, gb, None, ws, plan_ready=False,
+                                   ws_clean=(rep == 1 or name == "recompute"), **kw)
+            torch.cuda.synchronize()
+        res[name] = (gt, gb)
+    tol = TOL[dtype]
+    assert nerr(out, want_out) <= tol
+    for name, (gt, gb) in res.items():
+        assert nerr(gt, want["E_tok"]) <= tol, f"{name} gE_tok {nerr(gt, want['E_tok']):.3e}"
+        assert nerr(gb, want["E_byte"]) <= tol, f"{name} gE_byte {nerr(gb, want['E_byte']):.3e}"
+    untouched = torch.ones(V, dtype=torch.bool)
+    untouched[toks.long()] = False
+    if untouched.any():
+        assert float(res["saved"][0][untouched.to(d)].abs().max()) == 0.0
+
+
 def test_unsupported_and_bad_arguments():
     import mot_b200
     d = dev()
