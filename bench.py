@@ -285,14 +285,16 @@ def run_ours(args):
     out = torch.empty(N, Do, dtype=dt, device=dev)
     # what F.rms_norm's autograd node keeps: the forward result and rstd (read by the saved-output backward of the
     # MoT-sum variant; the other variants rebuild the mixed row and ignore them)
-    rstd = torch.empty(N, dtype=torch.float32, device=dev) if (w["variant"] == "V3" and not os.environ.get("MOT_NO_SAVED_BWD")) else None
+    rstd = None   # allocated below once the descriptor exists: only where the library would use it
     # one flat gradient bucket [gE_tok | gE_byte] the backward writes into -> a single NCCL all-reduce
     from mot_b200 import dp
     bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False)],
-                           symmetric=(world > 1 and not os.environ.get("MOT_DP_NCCL")))
+                           symmetric="auto" if world > 1 else False)
     gE_tok, gE_byte = bucket.views()
     g_lam = torch.empty(2, dtype=torch.float32, device=dev) if lam is not None else None
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
+    if ops.embed_bwd_uses_saved(desc):
+        rstd = torch.empty(N, dtype=torch.float32, device=dev)
     ws = ops.acquire_workspace(desc, dev)   # kept across steps: every completed backward leaves it clean (no memset)
     main_stream = torch.cuda.current_stream(dev)
 

@@ -174,6 +174,11 @@ int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_i
                         const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte, float* g_lam,
                         void* workspace, size_t ws_bytes, int32_t ws_flags, void* stream);
 
+/* 1 when mot_embed_bwd_saved would use out_saved / rstd_saved for this descriptor (so a caller knows whether keeping
+ * them pays), else 0: only the MoT-sum variant, widths 512 / 768 / 1024, and at most 4 positions per vocabulary row
+ * (beyond that the token rows of the recompute kernel are L2 hits and it is the faster one). */
+int mot_embed_bwd_uses_saved(const MotDesc* d);
+
 /* ---- data-parallel exchange: average the gradient bucket across ranks through NVLink / NVSwitch (NVLS) -----------
  * Replaces the per-parameter dist.all_reduce(param.grad, AVG) of spt/train_gpt.py:1320-1321 and runs/7:697-700 for the
  * tensors this path owns.  `multicast_ptr` is the multicast mapping of the same symmetric-memory buffer on every rank

@@ -14,10 +14,11 @@
 
 namespace mot {
 
-// Few, fat CTAs: the switch round trip is microseconds and the link saturates with a few MB in flight; more CTAs only
-// add contention (8 ranks, 77 MB bf16: 36 x 1024 threads 215 us, 144 x 512 239 us, NCCL 270 us; gpurun_out/exp_nvls8.log).
+// Few, fat CTAs: the switch round trip is microseconds and the links saturate with about 1 MB in flight per rank; more
+// CTAs only add contention inside the switch (8 ranks, 77 MB bf16: 8 x 1024 threads 195 us, 16 x 1024 203 us, 36 x 1024
+// 219 us, 144 x 512 239 us, NCCL 270 us; gpurun_out/run6.log, exp_nvls8.log).
 constexpr int kArThreads = 1024;
-constexpr int kArMaxBlocks = 36;    // signal-pad slots used: blocks x world uint32 (torch's pad is 9216 B = 2304 slots)
+constexpr int kArMaxBlocks = 8;     // signal-pad slots used: blocks x world uint32 (torch's pad is 9216 B = 2304 slots)
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

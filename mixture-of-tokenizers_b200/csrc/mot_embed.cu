@@ -336,6 +336,26 @@ extern "C" int mot_stream_wait_event(void* stream, void* event) {
   return MOT_OK;
 }
 
+// Would mot_embed_bwd_saved run the saved-output kernel for this descriptor?  (variant, width with an instantiation,
+// and few enough positions per vocabulary row, see below)
+static bool saved_path_applies(const MotDesc* d, const EmbedParams& p) {
+  static const bool no_saved = getenv("MOT_NO_SAVED_BWD") != nullptr;  // debug knob (A/B timing)
+  if (no_saved || concat_splits(d) || pick_mode(p, kBwdCW) != 1) return false;
+  const int cpl = p.Do / (32 * kBwdCW);
+  if (!(cpl == 4 || cpl == 6 || cpl == 8 || (d->dtype == MOT_F32 && cpl == 2))) return false;
+  // Beyond ~4 positions per vocabulary row the recompute kernel wins: its token rows are re-read from L2 (the
+  // sorted stream visits a row's occurrences back to back) while the saved rows are all distinct HBM reads
+  // (768 = 16 x 48 bf16, V = 50257: 131K tokens 118 vs 132 us, 262K 225 vs 218 us, 1M 921 vs 795 us; gpurun_out/run4.log).
+  return p.N <= 4LL * p.V;
+}
+
+extern "C" int mot_embed_bwd_uses_saved(const MotDesc* d) {
+  if (validate(d) != MOT_OK) return 0;
+  EmbedParams p;
+  fill_params(d, p);
+  return saved_path_applies(d, p) ? 1 : 0;
+}
+
 extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                              void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
@@ -402,13 +422,9 @@ extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const v
     }
   } else {
     // the MoT-sum variant with the forward result kept: the saved-output kernel (mot_embed_bwd_sum.cuh); every other
-    // case, or no instantiation for this width, recomputes the mixed row
-    static const bool no_saved = getenv("MOT_NO_SAVED_BWD") != nullptr;  // debug knob (A/B timing)
+    // case recomputes the mixed row
     rc = -1;
-    // Beyond ~4 positions per vocabulary row the recompute kernel wins: its token rows are re-read from L2 (the
-    // sorted stream visits a row's occurrences back to back) while the saved rows are all distinct HBM reads
-    // (768 = 16 x 48 bf16, V = 50257: 131K tokens 118 vs 132 us, 262K 225 vs 218 us, 1M 921 vs 795 us; gpurun_out/run4.log).
-    if (out_saved && rstd_saved && !no_saved && p.N <= 4LL * p.V) {
+    if (out_saved && rstd_saved && saved_path_applies(d, p)) {
       if (!aligned16(out_saved)) return MOT_ERR_MISALIGNED;
       p.out_saved = out_saved;
       p.rstd = rstd_saved;

@@ -556,7 +556,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
   const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
   const T* gout = reinterpret_cast<const T*>(p.gout);
   const uint32_t g_bytes = (uint32_t)p.Do * sizeof(T);
-  const uint32_t t_bytes = has_tok ? (uint32_t)p.Dt * sizeof(T) : 0u;
+  // the token row itself is only needed where the backward goes through a norm or a lambda (a plain gather, e.g. the
+  // value embeddings of runs/7:308, has d E[v] = sum of the upstream rows: R = 0 in SURVEY 8d's byte count)
+  const bool need_trow = has_tok && (C::tok_norm(p) || C::out_norm(p) || C::has_lam(p));
+  const uint32_t t_bytes = need_trow ? (uint32_t)p.Dt * sizeof(T) : 0u;
 
   // ---- the warp's share of the token-sorted stream: chunks gw, gw+W, ... of R entries (gw is interleaved over the
   //      CTAs, so every SM gets the same number of chunks +-1), walked in batches of 32 entries (one per lane) ----
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       unsigned char* st = ring + (size_t)is * L.stage_bytes;
       mbar_expect_tx(bars + is, g_bytes + t_bytes);
       bulk_g2s(st, gout + (size_t)pos * p.io_ld + p.io_col, g_bytes, bars + is);
-      if (has_tok) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + is);
+      if (need_trow) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + is);
     }
     ++issued;
     if (++is == D) is = 0;

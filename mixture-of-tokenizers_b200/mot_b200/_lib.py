@@ -56,6 +56,7 @@ _SIGNATURES = {
     "mot_embed_fwd_save": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mot_embed_bwd_saved": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                       C.c_int32, _P]),
+    "mot_embed_bwd_uses_saved": (C.c_int, [C.POINTER(MotDesc)]),
     "mot_dp_allreduce_avg": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_uint32, _P]),
     "mot_pull_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "mot_pull": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,

@@ -29,16 +29,34 @@ def broadcast_params(params: Iterable[torch.Tensor], src: int = 0, group=None) -
         dist.broadcast(p.detach(), src, group=group)
 
 
+def own_allreduce_pays(group=None) -> bool:
+    """Whether the library's NVLS all-reduce beats NCCL for the gradient bucket of this path (77 MB bf16 at the
+    124M shape).  Measured on 8xB200 / NVSwitch (gpurun_out/exp_nvls8.log, run5.log): 8 ranks 215 us vs NCCL 270 us;
+    4 ranks 235 vs 214 us; 2 ranks 226 vs 174 us.  Through the switch every rank moves S*(1 + 1/n) bytes per
+    direction (its own slice also travels to the switch and back), NCCL's ring 2*S*(n-1)/n: the in-switch reduction
+    wins from n = 8 on.  MOT_DP_OWN=1 / MOT_DP_NCCL=1 force either."""
+    if os.environ.get("MOT_DP_NCCL"):
+        return False
+    if os.environ.get("MOT_DP_OWN"):
+        return True
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    return dist.get_world_size(group) >= 8
+
+
 class GradBucket:
     """One flat buffer holding the gradients of `params` back to back (each slice 16-byte aligned), with a view per
     parameter.  `views()` are handed to the backward kernels as their dense-gradient outputs (mot_embed_bwd
     overwrites every row, so no zeroing is needed), `attach()` points `param.grad` at them, `all_reduce_avg()`
     averages the whole bucket across ranks in one collective."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric: bool = False,
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric=False,
                  group=None):
         """symmetric=True (CUDA, initialised NCCL group): allocate the bucket in symmetric memory with a multicast
-        mapping so that all_reduce_avg() runs the library's own NVLS kernel (mot_dp_allreduce_avg) instead of NCCL."""
+        mapping so that all_reduce_avg() runs the library's own NVLS kernel (mot_dp_allreduce_avg) instead of NCCL.
+        symmetric="auto": do that where the kernel was measured faster than NCCL (own_allreduce_pays)."""
+        if symmetric == "auto":
+            symmetric = own_allreduce_pays(group)
         self.params: List[torch.nn.Parameter] = list(params)
         if not self.params:
             raise ValueError("GradBucket needs at least one parameter")

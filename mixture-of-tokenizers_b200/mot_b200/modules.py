@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .ops import MixSpec, mot_embed, mot_embed_proj
+from .ops import MixSpec, mot_embed, mot_embed_proj, tok_gather
 
 # variant name -> MixSpec kwargs (`slot_major` is the `.view(bpt,-1)` id layout of the sum runs)
 RUN_VARIANTS = {
@@ -56,7 +56,7 @@ class MoTEmbedding(nn.Module):
         single `bucket.all_reduce_avg()`.  Call after the module is on its device and in its final dtype."""
         from .dp import GradBucket
         tables = [m.weight for m in (self.embed_tokens, self.embed_bytes) if m is not None]
-        self.grad_bucket = bucket if bucket is not None else GradBucket(tables)
+        self.grad_bucket = bucket if bucket is not None else GradBucket(tables, symmetric="auto")
         return self.grad_bucket
 
     def forward(self, token_inputs: torch.Tensor, byte_inputs: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -121,6 +121,79 @@ class MoTProjEmbedding(nn.Module):
         x = mot_embed_proj(token_inputs, byte_inputs, self.embed_tokens.weight, self.embed_bytes.weight,
                            self.byte_mixin_weight, self.spec, bpt=self.bpt)
         return x[None]
+
+
+class MoTSplitResidualEmbedding(nn.Module):
+    """runs/71081:302-304,315 (V3g): the token and byte halves are kept apart for the per-block residuals.
+    forward(token_inputs [T], byte_inputs [bpt, T]) -> (x, x0t, x0b), each [1, T, model_dim], with
+    x0t = norm(embed_tokens(tok)), x0b = the per-byte-normed bytes concatenated in the `.view(bpt,-1)` order and
+    x = lam_tok * x0t + lam_byte * x0b.  Parameters `embed_tokens.weight`, `embed_bytes.weight`, `lambdas` ([byte,
+    token] = the reference's scalars[-2], scalars[-1]).  Three launches of the fused kernel (V3c, token half, byte
+    half); autograd adds the dense gradients of the three uses."""
+
+    def __init__(self, token_vocab_size: int, byte_vocab_size: int, model_dim: int, byte_dim: int, bytes_per_token: int = 16):
+        super().__init__()
+        if byte_dim * bytes_per_token != model_dim:
+            raise ValueError("MoTSplitResidualEmbedding: bytes_per_token * byte_dim must equal model_dim (runs/71081:500-501)")
+        self.bpt = bytes_per_token
+        self.embed_tokens = nn.Embedding(token_vocab_size, model_dim)
+        self.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim)
+        self.lambdas = nn.Parameter(torch.tensor([0.5, 0.5]))
+
+    def forward(self, token_inputs: torch.Tensor, byte_inputs: torch.Tensor):
+        assert token_inputs.ndim == 1
+        Et, Eb = self.embed_tokens.weight, self.embed_bytes.weight
+        x0t = mot_embed(token_inputs, None, Et, None, MixSpec(combine="tok_only", tok_norm=True, out_norm=False))
+        x0b = mot_embed(None, byte_inputs, None, Eb,
+                        MixSpec(combine="bytes_only", byte_norm=True, out_norm=False, slot_major=True), bpt=self.bpt)
+        x = mot_embed(token_inputs, byte_inputs, Et, Eb, MixSpec(**RUN_VARIANTS["V3c"]), bpt=self.bpt,
+                      lam=self.lambdas.flip(0))
+        return x[None], x0t[None], x0b[None]
+
+
+class TokenValueEmbeddings(nn.Module):
+    """The value embeddings that share the token ids with the embedding front: parameters
+    `value_embeds.{0,1,2}.weight` [vocab, model_dim] (runs/7:252; spt/train_gpt.py:566); forward(token_inputs) ->
+    `[value_embed(token_inputs) for value_embed in self.value_embeds]` (runs/7:308; spt/train_gpt.py:600).  One token
+    sort serves the three dense gradient scatters."""
+
+    def __init__(self, vocab_size: int, model_dim: int, n_tables: int = 3):
+        super().__init__()
+        self.value_embeds = nn.ModuleList([nn.Embedding(vocab_size, model_dim) for _ in range(n_tables)])
+
+    def forward(self, token_inputs: torch.Tensor):
+        outs = tok_gather(token_inputs, *[m.weight for m in self.value_embeds])
+        return [o.view(*token_inputs.shape, -1) for o in outs]
+
+
+class MoTValueEmbeddings(nn.Module):
+    """runs/9_mot-in_mot-valemb.py:252-254,311-313 (V6): three value embeddings, each a concat + projection mix of a
+    token table and a byte table.  Parameters `value_embeds_toks.{i}.weight` [token_vocab, token_dim],
+    `value_embeds_bytes.{i}.weight` [token_vocab, byte_dim] (the reference sizes the byte value tables by the TOKEN
+    vocabulary; only the first byte_vocab rows are ever indexed) and `value_byte_mixin_weights.{i}`
+    [token_dim, token_dim + bpt*byte_dim] bf16.  forward(token_inputs [T], byte_inputs [1, T*bpt]) -> list of three
+    [1, T, token_dim]."""
+
+    def __init__(self, token_vocab_size: int, byte_vocab_size: int, token_dim: int, byte_dim: int,
+                 bytes_per_token: int = 16, n_tables: int = 3):
+        super().__init__()
+        self.bpt, self.byte_vocab = bytes_per_token, byte_vocab_size
+        self.value_embeds_toks = nn.ModuleList([nn.Embedding(token_vocab_size, token_dim) for _ in range(n_tables)])
+        self.value_embeds_bytes = nn.ModuleList([nn.Embedding(token_vocab_size, byte_dim) for _ in range(n_tables)])
+        self.value_byte_mixin_weights = nn.ParameterList(
+            [nn.Parameter(_init_linear_(torch.empty(token_dim, token_dim + bytes_per_token * byte_dim)).bfloat16())
+             for _ in range(n_tables)])
+        self.spec = MixSpec(**PROJ_VARIANTS["V1"])
+
+    def forward(self, token_inputs: torch.Tensor, byte_inputs: torch.Tensor):
+        assert token_inputs.ndim == 1
+        outs = []
+        for et, eb, w in zip(self.value_embeds_toks, self.value_embeds_bytes, self.value_byte_mixin_weights):
+            # rows >= byte_vocab of the byte value table are never gathered: hand the kernels the live rows (autograd
+            # pads their gradient back to the full table with zeros, like the reference's dense embedding backward)
+            outs.append(mot_embed_proj(token_inputs, byte_inputs, et.weight, eb.weight[:self.byte_vocab], w, self.spec,
+                                       bpt=self.bpt)[None])
+        return outs
 
 
 class _Holder(nn.Module):

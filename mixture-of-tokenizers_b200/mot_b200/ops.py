@@ -195,6 +195,11 @@ def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, s
     L.check(rc, "mot_embed_fwd")
 
 
+def embed_bwd_uses_saved(desc: L.MotDesc) -> bool:
+    """Whether mot_embed_bwd_saved would read the kept forward result for this descriptor (MoT-sum, moderate N)."""
+    return bool(L.lib().mot_embed_bwd_uses_saved(desc))
+
+
 def embed_workspace_bytes(desc: L.MotDesc) -> int:
     return int(L.lib().mot_embed_workspace_bytes(desc))
 
@@ -348,8 +353,7 @@ class _MotEmbedFn(torch.autograd.Function):
             embed_plan_async(desc, tok, ctx.ws, dev, st)
         # MoT-sum (runs/71): keep what rms_norm's autograd node keeps (its result and rstd); the backward then reads two
         # rows per occurrence instead of rebuilding the mixed row (mot_embed_bwd_saved)
-        keep = needs_grad and n > 0 and spec.combine == "add" and spec.out_norm and lam is None \
-            and not (spec.tok_norm or spec.byte_norm)
+        keep = needs_grad and n > 0 and bool(L.lib().mot_embed_bwd_uses_saved(desc))
         rstd = torch.empty(n, dtype=torch.float32, device=dev) if keep else None
         embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st, rstd=rstd)
         ctx.desc, ctx.dev = desc, dev
@@ -412,6 +416,79 @@ def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], 
     ((param, view), (param, view)) pairs for the token / byte table: the backward writes the dense gradient into `view`
     (a slice of a dp.GradBucket) and installs it as `param.grad`."""
     return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam, grad_bufs)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# several tables gathered with the same token ids (the value embeddings, runs/7:252,308; spt/train_gpt.py:566,600)
+# ------------------------------------------------------------------------------------------------------------
+class _TokGatherFn(torch.autograd.Function):
+    """outs[i] = tables[i][tokens]: plain gathers (no norm) of same-shaped tables.  The backward needs the positions
+    grouped by token id once for all tables: one sort plan (started beside the first forward gather), one scatter
+    launch per table reusing it (MOT_WS_PLAN_READY); the dense gradients need no token rows (R = 0)."""
+
+    @staticmethod
+    def forward(ctx, tokens, *tables):
+        dev = _require_cuda(tokens, *tables)
+        if not tables:
+            raise RuntimeError("mot_b200.tok_gather: need at least one table")
+        shape, dtype = tables[0].shape, tables[0].dtype
+        for E in tables:
+            if E.shape != shape or E.dtype != dtype or E.dim() != 2:
+                raise NotImplementedError("mot_b200.tok_gather: tables must share one [V, D] shape and dtype")
+        tok = tokens.reshape(-1)
+        tok = (tok if tok.dtype == torch.int32 else tok.to(torch.int32)).contiguous()
+        n = tok.numel()
+        spec = MixSpec(combine="tok_only", out_norm=False)
+        Es = [E.contiguous() for E in tables]
+        desc = make_desc(spec, n, Es[0], None, 0, ids=None, ttb=None, has_lam=False)
+        ctx.ws = None
+        st = _stream(dev)
+        if any(ctx.needs_input_grad[1:]) and n > 0:
+            ctx.ws = acquire_workspace(desc, dev)
+            embed_plan_async(desc, tok, ctx.ws, dev, st)
+        outs = []
+        for E in Es:
+            out = torch.empty((n, shape[1]), dtype=dtype, device=dev)
+            embed_forward_out(desc, tok, None, None, E, None, None, out, st)
+            outs.append(out)
+        ctx.desc, ctx.dev, ctx.n_tables = desc, dev, len(Es)
+        ctx.save_for_backward(tok, *Es)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        tok, *Es = ctx.saved_tensors
+        desc, dev = ctx.desc, ctx.dev
+        st = _stream(dev)
+        ws, planned = ctx.ws, ctx.ws is not None
+        if ws is None:
+            ws = acquire_workspace(desc, dev)
+        if planned:
+            embed_plan_join(ws, dev, st)
+            clean = True
+        else:
+            clean, ws.clean = ws.clean, False
+        grads = []
+        for i, (E, g) in enumerate(zip(Es, grad_outs)):
+            if g is None or not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            g = g.reshape(-1, E.shape[1]).to(E.dtype).contiguous()
+            gE = torch.empty_like(E)
+            embed_backward_out(desc, tok, None, None, E, None, None, g, gE, None, None, ws.buf,
+                               plan_ready=planned, ws_clean=clean, stream=st)
+            planned, clean = True, True     # the first scatter leaves the plan in place and the accumulators zeroed
+            grads.append(gE)
+        ws.clean = True
+        ctx.ws = None
+        release_workspace(ws)
+        return (None, *grads)
+
+
+def tok_gather(tokens: torch.Tensor, *tables: torch.Tensor):
+    """`[E(tokens) for E in tables]` (the value embeddings of runs/7:308 / spt/train_gpt.py:600): returns a tuple of
+    [n_tokens, D] tensors; dense gradients, one token sort shared by every table."""
+    return _TokGatherFn.apply(tokens, *tables)
 
 
 # ------------------------------------------------------------------------------------------------------------

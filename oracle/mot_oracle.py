@@ -390,3 +390,33 @@ def mot_embed_fwd_bwd(spec: MixSpec, tokens, byte_ids, E_tok, E_byte, grad_out, 
     out.backward(grad_out.detach().to(math_dtype).reshape(out.shape))
     grads = {k: (v.grad if v is not None else None) for k, v in params.items()}
     return out.detach(), grads
+
+
+def value_embeds_fwd_bwd(tokens, tables, grad_outs, math_dtype=torch.float32):
+    """The value embeddings gathered with the token ids (runs/7:252,308: `ve = [value_embed(token_inputs) for
+    value_embed in self.value_embeds]`; spt/train_gpt.py:566,600) and their dense gradients
+    (embedding_dense_backward: duplicates accumulate, rows never gathered are zero).  Returns (outs, grads)."""
+    tokens = tokens.reshape(-1).long()
+    leaves = [E.detach().to(math_dtype).clone().requires_grad_(True) for E in tables]
+    outs = [F.embedding(tokens, E) for E in leaves]
+    for o, g in zip(outs, grad_outs):
+        o.backward(g.detach().to(math_dtype).reshape(o.shape))
+    return [o.detach() for o in outs], [E.grad for E in leaves]
+
+
+def split_residual_fwd_bwd(tokens, byte_ids, E_tok, E_byte, lam_tok, lam_byte, grads, *, bpt=16,
+                           math_dtype=torch.float32, eps=None):
+    """runs/71081:302-304,315 (V3g): x0t = norm(embed_tokens(tok)); x0b = cat of the per-byte-normed rows of the
+    `[bpt, T]` id tensor; x = x0t * scalars[-1] + x0b * scalars[-2].  `grads` = upstream gradients of (x, x0t, x0b).
+    Returns ((x, x0t, x0b), dict of dense grads)."""
+    if eps is None:
+        eps = FP32_EPS
+    leaf = lambda t: t.detach().to(math_dtype).clone().requires_grad_(True)  # noqa: E731
+    Et, Eb, lt, lb = leaf(E_tok), leaf(E_byte), leaf(lam_tok), leaf(lam_byte)
+    tokens = tokens.reshape(-1).long()
+    n = tokens.numel()
+    x0t = rms_norm(F.embedding(tokens, Et), eps)
+    x0b = rms_norm(gather_byte_rows(Eb, byte_ids, n, bpt, True), eps).reshape(n, -1)
+    x = x0t * lt + x0b * lb
+    torch.autograd.backward([x, x0t, x0b], [g.detach().to(math_dtype).reshape(n, -1) for g in grads])
+    return (x.detach(), x0t.detach(), x0b.detach()), {"E_tok": Et.grad, "E_byte": Eb.grad, "lam_tok": lt.grad, "lam_byte": lb.grad}

@@ -112,3 +112,29 @@ def test_module_keeps_reference_parameter_names():
     assert "lambdas" in dict(m.named_parameters())
     with pytest.raises(NotImplementedError):
         mot_b200.MoTEmbedding(50257, 458, 1024, 64, 16, variant="cross_attn")
+
+
+def test_value_embedding_modules_keep_reference_names_and_refuse_cpu():
+    m = mot_b200.TokenValueEmbeddings(50257, 64)
+    assert [n for n, _ in m.named_parameters()] == [f"value_embeds.{i}.weight" for i in range(3)]   # runs/7:252
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(5, dtype=torch.int32))
+    m9 = mot_b200.MoTValueEmbeddings(1000, 458, 64, 16, 16)                                          # runs/9:252-254
+    names = [n for n, _ in m9.named_parameters()]
+    assert names[:3] == [f"value_embeds_toks.{i}.weight" for i in range(3)]
+    assert names[3:6] == [f"value_embeds_bytes.{i}.weight" for i in range(3)]
+    assert names[6:] == [f"value_byte_mixin_weights.{i}" for i in range(3)]
+    assert tuple(m9.value_byte_mixin_weights[0].shape) == (64, 64 + 16 * 16) and m9.value_byte_mixin_weights[0].dtype == torch.bfloat16
+    m81 = mot_b200.MoTSplitResidualEmbedding(1000, 458, 512, 32, 16)                                  # runs/71081
+    assert [n for n, _ in m81.named_parameters()] == ["lambdas", "embed_tokens.weight", "embed_bytes.weight"]
+    with pytest.raises(ValueError):
+        mot_b200.MoTSplitResidualEmbedding(1000, 458, 512, 48, 16)
+
+
+def test_saved_backward_query_needs_no_device():
+    lib = L.lib()
+    assert lib.mot_embed_bwd_uses_saved(desc()) == 1                       # MoT-sum 768 = 16 x 48, 48K tokens
+    assert lib.mot_embed_bwd_uses_saved(desc(n_tokens=1 << 20)) == 0      # > 4 positions per vocabulary row
+    assert lib.mot_embed_bwd_uses_saved(desc(flags=L.F_OUT_NORM | L.F_TOK_NORM)) == 0
+    assert lib.mot_embed_bwd_uses_saved(desc(combine=L.CONCAT, out_dim=768 + 16 * 48)) == 0
+    assert lib.mot_embed_bwd_uses_saved(desc(abi_version=9)) == 0

@@ -252,8 +252,8 @@ def test_full_size_properties():
     (torch.float32, 512, 64, 8, 333, 200, False),
     (torch.float32, 768, 48, 16, 5000, 1500, True),       # hot rows straddle stream chunks -> slot + finalize path
     (torch.float32, 1024, 32, 32, 2049, 50257, False),    # mostly single-occurrence rows, many empty rows
-    (torch.bfloat16, 768, 48, 16, 70001, 3000, True),     # R = 64: two batches per stream chunk, ragged tail
-    (torch.bfloat16, 1024, 64, 16, 4097, 900, False),
+    (torch.bfloat16, 768, 48, 16, 70001, 20000, True),    # R = 64: two batches per stream chunk, ragged tail
+    (torch.bfloat16, 1024, 64, 16, 4097, 1100, False),
     (torch.bfloat16, 512, 64, 8, 1, 10, False),
 ])
 def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V, zipf):
@@ -273,6 +273,9 @@ def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V,
     spec = mot_b200.MixSpec(combine="add", slot_major=True)
     tk, idd, Et, Eb, go = toks.to(d), ids.to(d), E_tok.to(d), E_byte.to(d), gout.to(d)
     desc = ops.make_desc(spec, N, Et, Eb, bpt, ids=idd, ttb=None, has_lam=False)
+    assert ops.embed_bwd_uses_saved(desc)                   # these shapes take the saved-output kernel
+    big = ops.make_desc(spec, 8 * V, Et, Eb, bpt, ids=idd, ttb=None, has_lam=False)
+    assert not ops.embed_bwd_uses_saved(big)                # > 4 positions per vocabulary row: recompute kernel
     out = torch.empty(N, Dt, dtype=dtype, device=d)
     rstd = torch.full((N,), float("nan"), dtype=torch.float32, device=d)
     ops.embed_forward_out(desc, tk, idd, None, Et, Eb, None, out, rstd=rstd)

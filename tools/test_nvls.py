@@ -35,8 +35,7 @@ for dtype, shapes in [(torch.bfloat16, [(50257, 768), (458, 48)]), (torch.float3
         return a.elapsed_time(e) / reps * 1e3
     t_own = timeit(b.all_reduce_avg)
     if dtype == torch.bfloat16 and os.environ.get("MOT_AR_SWEEP"):
-        for blocks, threads, unroll in [(8, 1024, 8), (16, 1024, 8), (24, 1024, 8), (36, 1024, 8), (48, 1024, 8), (72, 1024, 8),
-                                        (16, 1024, 4), (36, 1024, 4), (72, 512, 8), (36, 512, 8), (72, 256, 8)]:
+        for blocks, threads, unroll in [(8, 1024, 8), (16, 1024, 8), (24, 1024, 8), (36, 1024, 8), (16, 1024, 4), (24, 512, 8), (36, 512, 8)]:
             os.environ.update(MOT_AR_BLOCKS=str(blocks), MOT_AR_THREADS=str(threads), MOT_AR_UNROLL=str(unroll))
             t = timeit(b.all_reduce_avg)
             if rank == 0:
