@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MOT_B200_ABI_VERSION 2
+#define MOT_B200_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------- */
 enum {
@@ -88,6 +88,11 @@ typedef struct MotDesc {
   int32_t flags;       /* MOT_F_* */
   int32_t ttb_dtype;   /* MOT_TTB_* (only with MOT_F_IDS_FROM_TTB) */
   float eps;           /* rms_norm eps; the reference uses torch's default, finfo(float32).eps */
+  int64_t row_stride;  /* elements between consecutive rows of `out` (forward) / `grad_out` (backward); 0 = out_dim.
+                          With col_offset it lets a call produce or consume a column slice of wider rows, e.g. the
+                          token half of the [tok | bytes] operand next to mot_byte_pair_fwd's byte half. */
+  int32_t col_offset;  /* first column of this call's slice inside those rows (multiple of 8) */
+  int32_t reserved;    /* 0 */
 } MotDesc;
 
 const char* mot_strerror(int rc);
@@ -178,6 +183,24 @@ int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_i
  * them pays), else 0: only the MoT-sum variant, widths 512 / 768 / 1024, and at most 4 positions per vocabulary row
  * (beyond that the token rows of the recompute kernel are L2 hits and it is the faster one). */
 int mot_embed_bwd_uses_saved(const MotDesc* d);
+
+/* ---- byte half of `--add-padded-and-pulled` (spt/train_gpt.py:371-379) ----------------------------------------
+ * rows[pos, col_offset + k*byte_dim : +byte_dim] = rms_norm(E_byte[ids_a[pos,k]] + E_byte[ids_b[pos,k]]) for k < bpt:
+ * two gathers summed BEFORE the per-byte norm (`norm(self.embed_bytes(byte_tensor) + self.embed_bytes(byte_tensor_pulled))`).
+ * ids_a / ids_b: token-major [n_tokens, bpt] int32 or int64 (ids_i64).  Rows have `row_stride` elements: the byte
+ * columns of the [tok | bytes] projection operand, whose token columns mot_embed_fwd writes with MOT_TOK_ONLY and the
+ * same row_stride (MotDesc.row_stride / col_offset).  bpt <= 32, byte_dim a multiple of 8 with byte_dim <= 64 * G,
+ * G = the largest power of two <= 32 / bpt. */
+int mot_byte_pair_fwd(const void* ids_a, const void* ids_b, int32_t ids_i64, int64_t n_tokens, int32_t bpt,
+                      const void* E_byte, int32_t byte_vocab, int32_t byte_dim, int32_t dtype, float eps, void* out,
+                      int64_t row_stride, int32_t col_offset, void* stream);
+/* Backward: gE_byte [byte_vocab, byte_dim] dense, fully overwritten, = the norm backward of every (position, slot)
+ * added to BOTH gathered rows.  workspace: mot_byte_pair_workspace_bytes() bytes (cleared by the call). */
+size_t mot_byte_pair_workspace_bytes(int32_t byte_vocab, int32_t byte_dim);
+int mot_byte_pair_bwd(const void* ids_a, const void* ids_b, int32_t ids_i64, int64_t n_tokens, int32_t bpt,
+                      const void* E_byte, int32_t byte_vocab, int32_t byte_dim, int32_t dtype, float eps,
+                      const void* grad_out, int64_t row_stride, int32_t col_offset, void* gE_byte, void* workspace,
+                      size_t ws_bytes, void* stream);
 
 /* ---- data-parallel exchange: average the gradient bucket across ranks through NVLink / NVSwitch (NVLS) -----------
  * Replaces the per-parameter dist.all_reduce(param.grad, AVG) of spt/train_gpt.py:1320-1321 and runs/7:697-700 for the

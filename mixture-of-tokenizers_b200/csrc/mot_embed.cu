@@ -133,6 +133,11 @@ static int validate(const MotDesc* d) {
     case MOT_MEAN: if (d->byte_dim != d->tok_dim || d->out_dim != d->tok_dim) return MOT_ERR_BAD_ARG; break;
   }
   if (d->out_dim > 8 * 32 * 8) return MOT_ERR_UNSUPPORTED;  // CPL <= 8
+  if (d->row_stride != 0 || d->col_offset != 0) {  // a column slice of wider rows
+    const long long ld = d->row_stride ? d->row_stride : d->out_dim;
+    if (d->col_offset < 0 || ld < (long long)d->col_offset + d->out_dim) return MOT_ERR_BAD_ARG;
+    if (ld % 8 || d->col_offset % 8) return MOT_ERR_MISALIGNED;
+  }
   if ((d->flags & MOT_F_IDS_FROM_TTB) && has_bytes) {
     if (d->ttb_dtype < MOT_TTB_I16 || d->ttb_dtype > MOT_TTB_BF16) return MOT_ERR_UNSUPPORTED;
     if (d->flags & MOT_F_TTB_SCRAMBLE)
@@ -157,8 +162,8 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.flags = d->flags;
   p.ttb_dtype = d->ttb_dtype;
   p.n_chunks = d->out_dim / kChunk;
-  p.io_ld = d->out_dim;
-  p.io_col = 0;
+  p.io_ld = d->row_stride ? d->row_stride : d->out_dim;
+  p.io_col = d->col_offset;
   p.eps = d->eps;
   p.R = stream_chunk(d->n_tokens, kBwdThreads / 32);  // the saved-output kernel re-chunks for its own CTA size
   p.n_rep = kByteRep;
@@ -185,9 +190,9 @@ static void split_params(const MotDesc* d, EmbedParams& pt, EmbedParams& pb) {
   dbd.flags = d->flags & ~(MOT_F_TOK_NORM | MOT_F_BYTES_FIRST);
   fill_params(&dt, pt);
   fill_params(&dbd, pb);
-  pt.io_ld = pb.io_ld = d->out_dim;
-  pt.io_col = bytes_first ? db : 0;
-  pb.io_col = bytes_first ? 0 : d->tok_dim;
+  pt.io_ld = pb.io_ld = d->row_stride ? d->row_stride : d->out_dim;
+  pt.io_col = d->col_offset + (bytes_first ? db : 0);
+  pb.io_col = d->col_offset + (bytes_first ? 0 : d->tok_dim);
 }
 
 struct WsLayout {
@@ -340,7 +345,7 @@ extern "C" int mot_stream_wait_event(void* stream, void* event) {
 // and few enough positions per vocabulary row, see below)
 static bool saved_path_applies(const MotDesc* d, const EmbedParams& p) {
   static const bool no_saved = getenv("MOT_NO_SAVED_BWD") != nullptr;  // debug knob (A/B timing)
-  if (no_saved || concat_splits(d) || pick_mode(p, kBwdCW) != 1) return false;
+  if (no_saved || concat_splits(d) || pick_mode(p, kBwdCW) != 1 || p.io_ld != p.Do || p.io_col != 0) return false;
   const int cpl = p.Do / (32 * kBwdCW);
   if (!(cpl == 4 || cpl == 6 || cpl == 8 || (d->dtype == MOT_F32 && cpl == 2))) return false;
   // Beyond ~4 positions per vocabulary row the recompute kernel wins: its token rows are re-read from L2 (the

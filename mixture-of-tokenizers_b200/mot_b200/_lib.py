@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmot_b200" + os.environ.get("MOT_LIB_SUFFIX", "") + ".so")  # suffix: experiment builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # enums of include/mot_b200.h
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_MISALIGNED, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = range(7)
 BF16, F32 = 0, 1
@@ -32,6 +32,7 @@ class MotDesc(C.Structure):
         ("tok_dim", C.c_int32), ("byte_dim", C.c_int32), ("out_dim", C.c_int32),
         ("combine", C.c_int32), ("flags", C.c_int32), ("ttb_dtype", C.c_int32),
         ("eps", C.c_float),
+        ("row_stride", C.c_int64), ("col_offset", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -57,6 +58,11 @@ _SIGNATURES = {
     "mot_embed_bwd_saved": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                       C.c_int32, _P]),
     "mot_embed_bwd_uses_saved": (C.c_int, [C.POINTER(MotDesc)]),
+    "mot_byte_pair_fwd": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P,
+                                    C.c_int64, C.c_int32, _P]),
+    "mot_byte_pair_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mot_byte_pair_bwd": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P,
+                                    C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P]),
     "mot_dp_allreduce_avg": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_uint32, _P]),
     "mot_pull_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "mot_pull": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,

@@ -207,7 +207,8 @@ class SptByteMixEmbedding(nn.Module):
     has at spt/train_gpt.py:605-606.  State-dict keys match the reference: `embed.embed_tokens.weight`,
     `embed.embed_bytes.weight`, `byte_mixin.mixin.mixin.weight` (fp32 master, cast to bf16 per call like
     CastedLinear, gradient returned in fp32).  byte_mixin_method "noop" gives norm(embed_tokens(tokens)).
-    Refused (no fallback): cross_attn, byte self-attention, add_padded_and_pulled."""
+    add_padded_and_pulled=True sums the padded and the pulled byte rows before the per-byte norm (:371-379).
+    Refused (no fallback): cross_attn, byte self-attention."""
 
     def __init__(self, vocab_size: int, byte_vocab_size: int, token_dim: int, byte_dim: int, model_dim: int,
                  bytes_per_token: int = 16, byte_mixin_method: str = "concat", pull_in: bool = True,
@@ -218,9 +219,8 @@ class SptByteMixEmbedding(nn.Module):
                                       "not a gather/pool; it has no kernel here (no fallback)")
         if use_byte_self_attn:
             raise NotImplementedError("mot_b200: use_byte_self_attn=True is not supported (no fallback)")
-        if add_padded_and_pulled:
-            raise NotImplementedError("mot_b200: add_padded_and_pulled (spt/train_gpt.py:371-379) is not supported yet")
         self.method, self.bpt, self.pull_in = byte_mixin_method, bytes_per_token, pull_in
+        self.add_padded_and_pulled = bool(add_padded_and_pulled) and pull_in and byte_mixin_method == "concat"  # :334-341
         self.embed = _Holder()
         self.embed.embed_tokens = nn.Embedding(vocab_size, token_dim if byte_mixin_method != "noop" else model_dim)
         self.byte_mixin = _Holder()
@@ -241,8 +241,13 @@ class SptByteMixEmbedding(nn.Module):
         ids = byte_tensor_pulled if self.pull_in else byte_tensor   # _forward_bytes_pulled / _padded, :350-369
         if ids is None:
             raise RuntimeError("mot_b200: byte ids are required (byte_tensor_pulled with pull_in, else byte_tensor)")
+        ids2 = None
+        if self.add_padded_and_pulled:                              # _forward_bytes_padded_and_pulled, :371-379
+            if byte_tensor is None:
+                raise RuntimeError("mot_b200: add_padded_and_pulled needs byte_tensor and byte_tensor_pulled")
+            ids, ids2 = byte_tensor, byte_tensor_pulled
         x = mot_embed_proj(tokens, ids, self.embed.embed_tokens.weight, self.embed.embed_bytes.weight,
-                           self.byte_mixin.mixin.mixin.weight, self.spec, bpt=self.bpt)
+                           self.byte_mixin.mixin.mixin.weight, self.spec, bpt=self.bpt, byte_ids2=ids2)
         return x.view(B, S, -1)
 
 

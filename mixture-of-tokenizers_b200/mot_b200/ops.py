@@ -143,7 +143,8 @@ def pull_from_right(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: i
 
 
 def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Optional[torch.Tensor],
-              ttb: Optional[torch.Tensor], has_lam: bool, seq_len: int = 0) -> L.MotDesc:
+              ttb: Optional[torch.Tensor], has_lam: bool, seq_len: int = 0, row_stride: int = 0,
+              col_offset: int = 0) -> L.MotDesc:
     ref = E_tok if E_tok is not None else E_byte
     if ref.dtype not in _DTYPE:
         raise NotImplementedError(f"mot_b200: embedding dtype {ref.dtype} is not supported (bf16 / fp32 only)")
@@ -177,7 +178,7 @@ def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Opt
             flags |= L.F_IDS_I64 if ids.dtype == torch.int64 else 0
     return L.MotDesc(L.ABI_VERSION, _DTYPE[ref.dtype], n_tokens, seq_len,
                      E_tok.shape[0] if has_tok else 0, E_byte.shape[0] if has_bytes else 0, bpt if has_bytes else 0,
-                     Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps)
+                     Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps, row_stride, col_offset, 0)
 
 
 def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None,
@@ -560,6 +561,30 @@ def rmsnorm_backward_out(y, grad_out, dy, eps: float = FP32_EPS) -> None:
     L.check(rc, "mot_rmsnorm_bwd")
 
 
+def byte_pair_forward_out(ids_a, ids_b, bpt: int, E_byte, out, col_offset: int, eps: float = FP32_EPS) -> None:
+    """mot_byte_pair_fwd: out[:, col_offset + k*bd : +bd] = rms_norm(E_byte[ids_a[:, k]] + E_byte[ids_b[:, k]])
+    (spt/train_gpt.py:371-379), written into the byte columns of the [n, K] operand `out`."""
+    dev = _require_cuda(ids_a, ids_b, E_byte, out)
+    with _on_device(dev):
+        rc = L.lib().mot_byte_pair_fwd(_ptr(ids_a), _ptr(ids_b), 1 if ids_a.dtype == torch.int64 else 0, out.shape[0], bpt,
+                                       _ptr(E_byte), E_byte.shape[0], E_byte.shape[1], _DTYPE[E_byte.dtype], eps,
+                                       _ptr(out), out.stride(0), col_offset, _stream(dev))
+    L.check(rc, "mot_byte_pair_fwd")
+
+
+def byte_pair_backward_out(ids_a, ids_b, bpt: int, E_byte, grad_rows, col_offset: int, gE_byte, eps: float = FP32_EPS) -> None:
+    """mot_byte_pair_bwd: dense gE_byte from the byte columns of grad_rows [n, K]."""
+    dev = _require_cuda(ids_a, ids_b, E_byte, grad_rows, gE_byte)
+    need = int(L.lib().mot_byte_pair_workspace_bytes(E_byte.shape[0], E_byte.shape[1]))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    with _on_device(dev):
+        rc = L.lib().mot_byte_pair_bwd(_ptr(ids_a), _ptr(ids_b), 1 if ids_a.dtype == torch.int64 else 0, grad_rows.shape[0],
+                                       bpt, _ptr(E_byte), E_byte.shape[0], E_byte.shape[1], _DTYPE[E_byte.dtype], eps,
+                                       _ptr(grad_rows), grad_rows.stride(0), col_offset, _ptr(gE_byte), _ptr(ws),
+                                       ws.numel(), _stream(dev))
+    L.check(rc, "mot_byte_pair_bwd")
+
+
 class _MotEmbedProjFn(torch.autograd.Function):
     """out = f_out( [tok | bytes] . W^T + bias ): the fused gather builds the [n, K] operand (mot_embed_fwd, CONCAT),
     the projection runs on the tensor cores (mot_linear_fwd), the row norm after it is a separate HBM-bound pass over
@@ -567,8 +592,8 @@ class _MotEmbedProjFn(torch.autograd.Function):
     not kept for the backward: it is gathered again (0.1 ms against 0.7 ms of GEMMs, and n*K*2 bytes less to hold)."""
 
     @staticmethod
-    def forward(ctx, spec: MixSpec, bpt: int, tokens, byte_ids, E_tok, E_byte, W, bias):
-        dev = _require_cuda(tokens, byte_ids, E_tok, E_byte, W, bias)
+    def forward(ctx, spec: MixSpec, bpt: int, tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2=None):
+        dev = _require_cuda(tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2)
         cdt = E_tok.dtype                      # compute dtype of the chain: bf16, or fp32 on the TF32 tensor-core path
         if cdt not in (torch.bfloat16, torch.float32) or E_byte.dtype != cdt:
             raise NotImplementedError("mot_b200: token and byte tables must both be bf16 or both fp32")
@@ -581,9 +606,25 @@ class _MotEmbedProjFn(torch.autograd.Function):
         if ids.numel() != n * bpt:
             raise RuntimeError(f"mot_b200: byte ids have {ids.numel()} entries, expected {n}*{bpt}")
         E_tok_c, E_byte_c = E_tok.contiguous(), E_byte.contiguous()
-        a_spec = dataclasses.replace(spec, combine="concat", out_norm=False)
-        desc = make_desc(a_spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=None, has_lam=False)
-        K, Do = desc.out_dim, W.shape[0]
+        ids2 = None
+        if byte_ids2 is not None:
+            # `--add-padded-and-pulled` (spt/train_gpt.py:371-379): two gathers summed before the per-byte norm.  The
+            # token columns of the operand come from the fused kernel (tok-only, strided rows), the byte columns from
+            # the pair kernels.
+            if not spec.byte_norm or spec.slot_major or spec.bytes_first:
+                raise NotImplementedError("mot_b200: the padded+pulled sum exists only with per-byte norms, token-major "
+                                          "ids and [tok | bytes] order (spt/train_gpt.py:371-379,442-443)")
+            ids2 = byte_ids2.contiguous()
+            if ids2.dtype != ids.dtype or ids2.numel() != ids.numel():
+                raise RuntimeError("mot_b200: the two byte-id tensors must share dtype and size")
+            K = E_tok_c.shape[1] + bpt * E_byte_c.shape[1]
+            desc = make_desc(MixSpec(combine="tok_only", tok_norm=spec.tok_norm, out_norm=False, eps=spec.eps), n, E_tok_c,
+                             None, 0, ids=None, ttb=None, has_lam=False, row_stride=K, col_offset=0)
+        else:
+            a_spec = dataclasses.replace(spec, combine="concat", out_norm=False)
+            desc = make_desc(a_spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=None, has_lam=False)
+            K = desc.out_dim
+        Do = W.shape[0]
         if W.shape[1] != K:
             raise RuntimeError(f"mot_b200: projection weight is {tuple(W.shape)}, expected [{Do}, {K}]")
         w16 = W.detach().to(cdt).contiguous()                  # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
@@ -592,7 +633,11 @@ class _MotEmbedProjFn(torch.autograd.Function):
             ctx.ws = acquire_workspace(desc, dev)
             embed_plan_async(desc, tok, ctx.ws, dev)
         A = torch.empty((n, K), dtype=cdt, device=dev)
-        embed_forward_out(desc, tok, ids, None, E_tok_c, E_byte_c, None, A)
+        if ids2 is None:
+            embed_forward_out(desc, tok, ids, None, E_tok_c, E_byte_c, None, A)
+        elif n > 0:
+            embed_forward_out(desc, tok, None, None, E_tok_c, None, None, A)
+            byte_pair_forward_out(ids, ids2, bpt, E_byte_c, A, E_tok_c.shape[1], spec.eps)
         Y = torch.empty((n, Do), dtype=cdt, device=dev)
         b32 = bias.detach().float().contiguous() if bias is not None else None
         linear_forward_out(A, w16, Y, b32)
@@ -604,14 +649,15 @@ class _MotEmbedProjFn(torch.autograd.Function):
             out = Y
         ctx.desc, ctx.dev, ctx.spec = desc, dev, spec
         ctx.w_dtype, ctx.has_bias = W.dtype, bias is not None
-        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y)
+        ctx.pair, ctx.bpt, ctx.K = ids2 is not None, bpt, K
+        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y, ids2 if ids2 is not None else torch.empty(0))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        tok, ids, E_tok, E_byte, w16, Y = ctx.saved_tensors
+        tok, ids, E_tok, E_byte, w16, Y, ids2 = ctx.saved_tensors
         desc, dev, spec = ctx.desc, ctx.dev, ctx.spec
-        n, K, Do = tok.numel(), desc.out_dim, w16.shape[0]
+        n, K, Do = tok.numel(), ctx.K, w16.shape[0]
         cdt = Y.dtype
         g = grad_out.reshape(n, Do).to(cdt).contiguous()
         if spec.out_norm:
@@ -621,7 +667,11 @@ class _MotEmbedProjFn(torch.autograd.Function):
             dY = g
         g_bias = dY.float().sum(0) if ctx.has_bias else None
         A = torch.empty((n, K), dtype=cdt, device=dev)
-        embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)       # gathered again, not kept
+        if not ctx.pair:
+            embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)   # gathered again, not kept
+        elif n > 0:
+            embed_forward_out(desc, tok, None, None, E_tok, None, None, A)
+            byte_pair_forward_out(ids, ids2, ctx.bpt, E_byte, A, E_tok.shape[1], spec.eps)
         dW32 = torch.empty((Do, K), dtype=torch.float32, device=dev)
         dW16 = torch.empty((Do, K), dtype=torch.bfloat16, device=dev) if ctx.w_dtype == torch.bfloat16 else None
         linear_bwd_weight_out(dY, A, dW32, dW16)
@@ -636,23 +686,31 @@ class _MotEmbedProjFn(torch.autograd.Function):
             clean = True
         else:
             clean, ws.clean = ws.clean, False
-        embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, dA, gE_tok, gE_byte, None, ws.buf,
-                           plan_ready=planned, ws_clean=clean)
+        if not ctx.pair:
+            embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, dA, gE_tok, gE_byte, None, ws.buf,
+                               plan_ready=planned, ws_clean=clean)
+        else:   # token columns through the sorted-stream scatter, byte columns through the pair kernel
+            embed_backward_out(desc, tok, None, None, E_tok, None, None, dA, gE_tok, None, None, ws.buf,
+                               plan_ready=planned, ws_clean=clean)
+            byte_pair_backward_out(ids, ids2, ctx.bpt, E_byte, dA, E_tok.shape[1], gE_byte, spec.eps)
         ws.clean = True
         ctx.ws = None
         release_workspace(ws)
         gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
-        return None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None)
+        return (None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None),
+                None)
 
 
 def mot_embed_proj(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Tensor, E_byte: torch.Tensor,
-                   W: torch.Tensor, spec: MixSpec, *, bpt: int = 16, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   W: torch.Tensor, spec: MixSpec, *, bpt: int = 16, bias: Optional[torch.Tensor] = None,
+                   byte_ids2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Concat + dense projection variants: `norm(F.linear(cat([f(tok), f(bytes)]), W))` (runs/7:226-234, runs/72,
     spt/train_gpt.py:439-443).  spec.tok_norm / byte_norm are the per-input norms, spec.out_norm the norm after the
     projection, spec.bytes_first the operand order.  Tables bf16 with W bf16 (runs) or an fp32 master (spt: cast per
-    call, gradient returned in fp32); or everything fp32 (mathblations: TF32 tensor cores).  Returns
+    call, gradient returned in fp32); or everything fp32 (mathblations: TF32 tensor cores).  byte_ids2: the second id
+    tensor of `--add-padded-and-pulled` (spt/train_gpt.py:371-379), rows summed before the per-byte norm.  Returns
     [n_tokens, W.shape[0]] in the table dtype."""
-    return _MotEmbedProjFn.apply(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias)
+    return _MotEmbedProjFn.apply(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2)
 
 
 def launch_count() -> int:

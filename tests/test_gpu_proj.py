@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_KERNEL = 2.0 ** -8
 TOL_CHAIN = 2.0 ** -6
+TOL_TF32_CHAIN = 2.0 ** -8   # fp32 tables, TF32 products (10 mantissa bits) through projection + norm, fwd and bwd
 
 
 def dev():
@@ -169,9 +170,85 @@ def test_reference_golden_projection_through_cuda(golden_dir):
     assert nerr(m.byte_mixin.mixin.mixin.weight.grad, torch.from_numpy(s[f"{tag}_gW"])) <= TOL_CHAIN
 
 
+@pytest.mark.parametrize("dtype,bpt,bd,N", [
+    (torch.float32, 16, 48, 301), (torch.float32, 18, 56, 77), (torch.float32, 20, 64, 130), (torch.float32, 4, 8, 33),
+    (torch.float32, 32, 32, 65), (torch.bfloat16, 8, 128, 40),
+    (torch.bfloat16, 16, 48, 4097), (torch.bfloat16, 18, 32, 513), (torch.bfloat16, 16, 64, 1),
+])
+def test_byte_pair_kernels_match_oracle(dtype, bpt, bd, N):
+    """mot_byte_pair_fwd / _bwd (spt/train_gpt.py:371-379: norm(embed_bytes(padded) + embed_bytes(pulled))) written into
+    / read from the byte columns of wider rows, against the oracle's byte_ids2 path; int64 ids like spt."""
+    from mot_b200 import ops
+    d = dev()
+    g = torch.Generator().manual_seed(bpt * 100 + bd)
+    Vb, Dt = 458, 64
+    K = Dt + bpt * bd
+    ia = torch.randint(0, Vb, (N, bpt), generator=g)
+    ib = torch.randint(0, Vb, (N, bpt), generator=g)
+    ib[::3] = ia[::3]                      # equal ids in both tensors (pad/pad): both REDs hit the same row
+    E = torch.randn(Vb, bd, generator=g).to(dtype)
+    gout = torch.randn(N, bpt * bd, generator=g).to(dtype)
+    spec = O.MixSpec(combine="bytes_only", byte_norm=True, out_norm=False)
+    want_out, want = O.mot_embed_fwd_bwd(spec, torch.zeros(N, dtype=torch.int64), ia, None, E, gout, bpt=bpt, byte_ids2=ib)
+    A = torch.full((N, K), 7.0, dtype=dtype, device=d)
+    ops.byte_pair_forward_out(ia.to(d), ib.to(d), bpt, E.to(d), A, Dt)
+    tol = 1e-5 if dtype == torch.float32 else TOL_KERNEL
+    assert nerr(A[:, Dt:], want_out) <= tol
+    assert float((A[:, :Dt] - 7.0).abs().max()) == 0.0            # the token columns are not touched
+    dA = torch.zeros(N, K, dtype=dtype, device=d)
+    dA[:, Dt:] = gout.to(d)
+    gE = torch.full((Vb, bd), float("nan"), dtype=dtype, device=d)
+    ops.byte_pair_backward_out(ia.to(d), ib.to(d), bpt, E.to(d), dA, Dt, gE)
+    assert nerr(gE, want["E_byte"]) <= tol, f"{nerr(gE, want['E_byte']):.3e}"
+    ops.byte_pair_backward_out(ia.to(d).int(), ib.to(d).int(), bpt, E.to(d), dA, Dt, gE)   # int32 ids, fresh workspace
+    assert nerr(gE, want["E_byte"]) <= tol
+
+
+def test_spt_add_padded_and_pulled_matches_reference_golden_and_oracle(golden_dir):
+    """`--add-padded-and-pulled` (spt/train_gpt.py:371-379,949-951) end to end through SptByteMixEmbedding: the
+    reference's own fp32 output / gradients (TF32 tensor cores here), then bf16 at the spt default dims vs the oracle."""
+    import mot_b200
+    d = dev()
+    s = np.load(os.path.join(golden_dir, "spt_float.npz"))
+    tag = "concat_addpp_f32"
+    Dt, bd = s[f"{tag}_E_tok"].shape[1], s[f"{tag}_E_byte"].shape[1]
+    Do, K = s[f"{tag}_W"].shape
+    bpt = (K - Dt) // bd
+    m = mot_b200.SptByteMixEmbedding(s[f"{tag}_E_tok"].shape[0], 458, Dt, bd, Do, bpt, pull_in=True,
+                                     add_padded_and_pulled=True).to(d)
+    with torch.no_grad():
+        m.embed.embed_tokens.weight.copy_(torch.from_numpy(s[f"{tag}_E_tok"]))
+        m.embed.embed_bytes.weight.copy_(torch.from_numpy(s[f"{tag}_E_byte"]))
+        m.byte_mixin.mixin.mixin.weight.copy_(torch.from_numpy(s[f"{tag}_W"]))
+    out = m(torch.from_numpy(s[f"{tag}_tokens"]).to(d), torch.from_numpy(s[f"{tag}_bytes_padded"]).to(d),
+            torch.from_numpy(s[f"{tag}_bytes_pulled"]).to(d))
+    out.backward(torch.from_numpy(s[f"{tag}_gout"]).to(d))
+    assert nerr(out, torch.from_numpy(s[f"{tag}_out"])) <= TOL_TF32_CHAIN
+    assert nerr(m.embed.embed_tokens.weight.grad, torch.from_numpy(s[f"{tag}_gE_tok"])) <= TOL_TF32_CHAIN
+    assert nerr(m.embed.embed_bytes.weight.grad, torch.from_numpy(s[f"{tag}_gE_byte"])) <= TOL_TF32_CHAIN
+    assert nerr(m.byte_mixin.mixin.mixin.weight.grad, torch.from_numpy(s[f"{tag}_gW"])) <= TOL_TF32_CHAIN
+
+    g = torch.Generator().manual_seed(17)
+    V, Vb, Dt, bd, Do, bpt, B, S = 700, 458, 256, 48, 1024, 16, 2, 300
+    m = mot_b200.SptByteMixEmbedding(V, Vb, Dt, bd, Do, bpt, pull_in=True, add_padded_and_pulled=True).to(d)
+    m.embed.bfloat16()
+    toks = torch.randint(0, V, (B, S), generator=g, dtype=torch.int32)
+    pad = torch.randint(0, Vb, (B, S * bpt), generator=g)
+    pul = torch.randint(0, Vb, (B, S * bpt), generator=g)
+    gout = torch.randn(B, S, Do, generator=g).bfloat16()
+    out = m(toks.to(d), pad.to(d), pul.to(d))
+    out.backward(gout.to(d))
+    Et, Eb, W = (t.detach().cpu() for t in (m.embed.embed_tokens.weight, m.embed.embed_bytes.weight, m.byte_mixin.mixin.mixin.weight))
+    want_out, want = O.mot_embed_fwd_bwd(O.VARIANTS["V1"][0], toks, pad, Et, Eb, gout, bpt=bpt, W=W.bfloat16(), byte_ids2=pul)
+    assert nerr(out.view(-1, Do), want_out) <= TOL_CHAIN
+    assert nerr(m.embed.embed_tokens.weight.grad, want["E_tok"]) <= TOL_CHAIN
+    assert nerr(m.embed.embed_bytes.weight.grad, want["E_byte"]) <= TOL_CHAIN
+    assert nerr(m.byte_mixin.mixin.mixin.weight.grad, want["W"]) <= TOL_CHAIN
+
+
 def test_spt_module_refuses_unsupported_options():
     import mot_b200
-    for kw in (dict(byte_mixin_method="cross_attn"), dict(use_byte_self_attn=True), dict(add_padded_and_pulled=True)):
+    for kw in (dict(byte_mixin_method="cross_attn"), dict(use_byte_self_attn=True)):
         with pytest.raises(NotImplementedError):
             mot_b200.SptByteMixEmbedding(100, 458, 64, 16, 128, 16, **kw)
 
