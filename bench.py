@@ -50,6 +50,11 @@ WORKLOADS = {
     # scaled-pre-train default (256/48 -> 1024, K = 1024, B=64 x S=1024 per GPU, spt/train_gpt.py:822)
     "mot-proj-runs7-64k": dict(variant="V1", N=65536, Dt=1024, bd=64, bpt=16, Do=1024, dtype="bf16"),
     "mot-proj-spt-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16"),
+    # scaled-pre-train with --add-padded-and-pulled (spt/train_gpt.py:371-379): two int64 id tensors, rows summed before
+    # the per-byte norm (mot_byte_pair_*), same projection
+    "mot-proj-spt-addpp-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16", pair=True),
+    # the three value embeddings gathered with the same token ids (runs/7:252,308), dense grads
+    "value-embeds-64k": dict(variant="VE", N=65536, Dt=1024, bd=0, bpt=0, dtype="bf16", tables=3),
     # BASELINE.json configs[1]: mathblations digit mixin (mathblations/model.py:256-268): B=1024, S=11, dpt 4,
     # vocab 10003, 256/256 -> K = 1280 -> 256, fp32 parameters, TF32 matmul; launch-latency bound
     "mathblations-concat": dict(variant="V8", N=1024 * 11, Dt=256, bd=256, bpt=4, Do=256, dtype="f32"),
@@ -184,8 +189,14 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_step_fn(w, n_sample, seed=12345):
     from oracle import mot_oracle as O
-    spec = O.VARIANTS[w["variant"]][0]
     g = torch.Generator().manual_seed(seed)
+    if w["variant"] == "VE":   # the value embeddings: plain gathers + dense grads (runs/7:252,308)
+        dt = torch.bfloat16
+        toks = torch.randint(0, V_TOK - 1, (n_sample,), generator=g, dtype=torch.int32)
+        tables = [torch.randn(V_TOK, w["Dt"], generator=g).to(dt) for _ in range(w["tables"])]
+        gouts = [torch.randn(n_sample, w["Dt"], generator=g).to(dt) for _ in range(w["tables"])]
+        return lambda: O.value_embeds_fwd_bwd(toks, tables, gouts, math_dtype=dt)
+    spec = O.VARIANTS[w["variant"]][0]
     Dt, bd, bpt = w["Dt"], w["bd"], w["bpt"]
     Do = algorithmic_bytes(w)[2]
     dt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
@@ -202,6 +213,8 @@ def cpu_reference_step_fn(w, n_sample, seed=12345):
         kw["W"] = ((torch.rand(w["Do"], K, generator=g) * 2 - 1) * (3 ** 0.5) * 0.5 * K ** -0.5).to(dt)
     if w["variant"] in ("V3c", "V3d"):
         kw["lam_tok"], kw["lam_byte"] = torch.tensor(0.5), torch.tensor(0.5)
+    if w.get("pair"):
+        kw["byte_ids2"] = torch.randint(0, V_BYTE, (1, n_sample * bpt), generator=g, dtype=torch.int32)
 
     def step():
         # the reference computes in the parameter dtype (eager bf16); math_dtype=dt reproduces that cost
@@ -465,9 +478,33 @@ def run_proj(args):
     ids = torch.randint(0, V_BYTE, (1, N * bpt), generator=gd, device=dev, dtype=torch.int32)
     ids_host = ids.cpu().pin_memory()
     gout = torch.randn(N, Do, generator=gd, device=dev).to(dt)
-    spec = mot_b200.MixSpec(combine="concat", tok_norm=True, byte_norm=True, out_norm=False)   # the [tok | bytes] operand
-    desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=False)
+    pair = bool(w.get("pair"))
+    if pair:   # spt ids are int64 [B, S*bpt]; the token columns come from a tok-only launch over strided rows
+        ids = ids.long()
+        ids2 = torch.randint(0, V_BYTE, (1, N * bpt), generator=gd, device=dev)
+        ids_host, ids2_host = ids.cpu().pin_memory(), ids2.cpu().pin_memory()
+        spec = mot_b200.MixSpec(combine="tok_only", tok_norm=True, out_norm=False)
+        desc = ops.make_desc(spec, N, E_tok, None, 0, ids=None, ttb=None, has_lam=False, row_stride=K, col_offset=0)
+    else:
+        spec = mot_b200.MixSpec(combine="concat", tok_norm=True, byte_norm=True, out_norm=False)   # the [tok | bytes] operand
+        desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=False)
     ws = ops.acquire_workspace(desc, dev)
+
+    def gather_A():
+        if pair:
+            ops.embed_forward_out(desc, tok, None, None, E_tok, None, None, A)
+            ops.byte_pair_forward_out(ids, ids2, bpt, E_byte, A, Dt)
+        else:
+            ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)
+
+    def scatter_dA():
+        if pair:
+            ops.embed_backward_out(desc, tok, None, None, E_tok, None, None, A, gE_tok, None, None, ws.buf,
+                                   plan_ready=True, ws_clean=True)
+            ops.byte_pair_backward_out(ids, ids2, bpt, E_byte, A, Dt, gE_byte)
+        else:
+            ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, A, gE_tok, gE_byte, None, ws.buf,
+                                   plan_ready=True, ws_clean=True)
     A = torch.empty(N, K, dtype=dt, device=dev)
     Y, out, dY = (torch.empty(N, Do, dtype=dt, device=dev) for _ in range(3))
     dW32 = torch.empty(Do, K, dtype=torch.float32, device=dev)
@@ -486,17 +523,16 @@ def run_proj(args):
     def step(record=False):
         # forward: fused gather of [tok | bytes] -> tcgen05 projection -> rms_norm   (runs/7:317-319,233-234)
         ops.embed_plan_async(desc, tok, ws, dev)
-        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)
+        gather_A()
         timed("fwd", lambda: ops.linear_forward_out(A, W, Y), record)
         ops.rmsnorm_forward_out(Y, out)
         # backward: norm bwd -> dW, dX on the tensor cores -> fused scatter into the dense table gradients
         ops.rmsnorm_backward_out(Y, gout, dY)
-        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)      # operand gathered again, not kept
+        gather_A()                                                                # operand gathered again, not kept
         timed("dw", lambda: ops.linear_bwd_weight_out(dY, A, dW32, gW), record)
         timed("dx", lambda: ops.linear_bwd_input_out(dY, W, A), record)          # dX overwrites the operand buffer
         ops.embed_plan_join(ws, dev)
-        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, A, gE_tok, gE_byte, None, ws.buf,
-                               plan_ready=True, ws_clean=True)
+        scatter_dA()
         ws.clean = True
         if world > 1:
             bucket.all_reduce_avg()
@@ -535,13 +571,22 @@ def run_proj(args):
 
     e2e = None
     if not args.no_e2e:
-        mod = mot_b200.MoTProjEmbedding(V_TOK, V_BYTE, Dt, bd, Do, bpt, variant="V1").to(dev).to(dt)
+        if pair:
+            mod = mot_b200.SptByteMixEmbedding(V_TOK, V_BYTE, Dt, bd, Do, bpt, pull_in=True, add_padded_and_pulled=True).to(dev)
+            mod.embed.bfloat16()
+            mod.embed_bytes = mod.embed.embed_bytes
+        else:
+            mod = mot_b200.MoTProjEmbedding(V_TOK, V_BYTE, Dt, bd, Do, bpt, variant="V1").to(dev).to(dt)
         res_host = torch.empty(V_BYTE, bd, dtype=dt).pin_memory()
 
         def e2e_step():
             for p_ in mod.parameters():
                 p_.grad = None
-            x = mod(tok_host.to(dev, non_blocking=True), ids_host.to(dev, non_blocking=True))
+            if pair:
+                x = mod(tok_host.to(dev, non_blocking=True).view(64, -1), ids_host.to(dev, non_blocking=True).view(64, -1),
+                        ids2_host.to(dev, non_blocking=True).view(64, -1))
+            else:
+                x = mod(tok_host.to(dev, non_blocking=True), ids_host.to(dev, non_blocking=True))
             x.backward(gout.view_as(x))
             if world > 1:
                 for p_ in mod.parameters():
@@ -561,8 +606,10 @@ def run_proj(args):
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * N / float(t_e.item()), "unit": "tokens/s",
-               "h2d_bytes_per_step": tok_host.numel() * 4 + ids_host.numel() * 4, "d2h_bytes_per_step": res_host.numel() * 2,
-               "ms_per_step": float(t_e.item()) * 1e3, "api": "mot_b200.MoTProjEmbedding.forward + autograd backward", "steps": Ke}
+               "h2d_bytes_per_step": tok_host.numel() * 4 + ids_host.numel() * ids_host.element_size() * (2 if pair else 1),
+               "d2h_bytes_per_step": res_host.numel() * 2, "ms_per_step": float(t_e.item()) * 1e3,
+               "api": ("mot_b200.SptByteMixEmbedding(add_padded_and_pulled=True)" if pair else "mot_b200.MoTProjEmbedding") +
+                      ".forward + autograd backward", "steps": Ke}
 
     if rank == 0:
         peak, peak_src = measured_tensor_peak()
@@ -573,7 +620,9 @@ def run_proj(args):
             "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": K_steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["name"], "variant": "V1 concat+projection (runs/7:226-234,317-319)",
+            "config": {"workload": w["name"],
+                       "variant": ("V1b padded+pulled byte rows summed before the norm (spt/train_gpt.py:371-379,439-443)" if pair
+                                   else "V1 concat+projection (runs/7:226-234,317-319)"),
                        "tokens_per_gpu_per_step": N, "token_dim": Dt, "byte_dim": bd, "bytes_per_token": bpt, "in_dim": K,
                        "out_dim": Do, "token_dist": args.dist, "l2": "working set > 126 MB L2, no flush",
                        "parallelism": f"dp{world}" + (", one flat-bucket NCCL all-reduce(AVG) per step" if world > 1 else "")},
@@ -594,6 +643,110 @@ def run_proj(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_value_embeds(args):
+    """`ve = [value_embed(token_inputs) for value_embed in self.value_embeds]` (runs/7:252,308) forward and
+    the three dense gradient scatters, one token sort shared by all tables.  HBM bound."""
+    import mot_b200
+    from mot_b200 import ops, _lib
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("bench.py: the value-embeds workload is a single-GPU kernel measurement")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    w = workload_config(args)
+    N, D, T = w["N"], w["Dt"], w["tables"]
+    dt = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(12345)
+    tables = [torch.randn(V_TOK, D, generator=g, device=dev).to(dt) for _ in range(T)]
+    gouts = [torch.randn(N, D, generator=g, device=dev).to(dt) for _ in range(T)]
+    tok_host = make_tokens(N, args.dist, 12345).pin_memory()
+    tok = tok_host.to(dev)
+    outs = [torch.empty(N, D, dtype=dt, device=dev) for _ in range(T)]
+    grads = [torch.empty_like(E) for E in tables]
+    desc = ops.make_desc(mot_b200.MixSpec(combine="tok_only", out_norm=False), N, tables[0], None, 0, ids=None, ttb=None, has_lam=False)
+    ws = ops.acquire_workspace(desc, dev)
+
+    def step():
+        ops.embed_plan_async(desc, tok, ws, dev)
+        for E, o in zip(tables, outs):
+            ops.embed_forward_out(desc, tok, None, None, E, None, None, o)
+        ops.embed_plan_join(ws, dev)
+        for E, go, gE in zip(tables, gouts, grads):
+            ops.embed_backward_out(desc, tok, None, None, E, None, None, go, gE, None, None, ws.buf, plan_ready=True, ws_clean=True)
+        ws.clean = True
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    K = args.steps
+    sampler = ClockSampler(0)
+    sampler.start(); time.sleep(0.3)
+    mot_b200.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = mot_b200.launch_count()
+    ms_step = e0.elapsed_time(e1) / K
+    # instrumented pass: event pairs around the main backward kernel of every scatter (3 per step -> the last one wins;
+    # use one step per pair)
+    lib = _lib.lib()
+    bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in bwd_ev:
+        a.record(); b.record()
+    torch.cuda.synchronize()
+    for i in range(K):
+        ops.embed_plan_async(desc, tok, ws, dev)
+        ops.embed_plan_join(ws, dev)
+        lib.mot_profile_events(None, None, bwd_ev[i][0].cuda_event, bwd_ev[i][1].cuda_event)
+        ops.embed_backward_out(desc, tok, None, None, tables[0], None, None, gouts[0], grads[0], None, None, ws.buf,
+                               plan_ready=True, ws_clean=True)
+        lib.mot_profile_events(None, None, None, None)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / K
+    e = 2
+    A_bwd1 = N * (D * e + 8) + V_TOK * D * e          # one table: upstream rows + sorted stream in, dense gradient out (R = 0)
+    A_step = T * (N * (4 + 2 * D * e) + A_bwd1)       # forward: ids + table row in, row out
+    mod = mot_b200.TokenValueEmbeddings(V_TOK, D, T).to(dev).to(dt)
+    res_host = torch.empty(16, D, dtype=dt).pin_memory()
+
+    def e2e_step():
+        for p_ in mod.parameters():
+            p_.grad = None
+        ve = mod(tok_host.to(dev, non_blocking=True))
+        torch.autograd.backward(ve, gouts)
+        res_host.copy_(mod.value_embeds[0].weight.grad[:16], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    Ke = max(10, K // 4)
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    t_e = (time.perf_counter() - t0) / Ke
+    peak, peak_src = measured_peaks()
+    line = {"metric": "byte-mix embedding fwd+bwd tokens/sec", "value": N / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": 1,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], "variant": "value embeddings: 3 plain gathers sharing the token ids (runs/7:252,308)",
+                       "tokens_per_gpu_per_step": N, "tables": T, "dim": D, "token_dist": args.dist,
+                       "l2": "working set > 126 MB L2, no flush", "parallelism": "dp1"},
+            "step_hbm_gbs": A_step / (ms_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "mot_bwd_kernel (plain gather: no token rows)", "achieved": A_bwd1 / (bwd_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": A_bwd1 / (bwd_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": A_bwd1, "kernel_ms": bwd_ms, "peak_source": peak_src},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": N / t_e, "unit": "tokens/s", "h2d_bytes_per_step": tok_host.numel() * 4,
+                    "d2h_bytes_per_step": res_host.numel() * 2, "ms_per_step": t_e * 1e3,
+                    "api": "mot_b200.TokenValueEmbeddings.forward + autograd backward", "steps": Ke}}
+    print(json.dumps(line), flush=True)
 
 
 def run_mathblations(args):
@@ -670,5 +823,7 @@ if __name__ == "__main__":
         run_proj(a)
     elif WORKLOADS[a.workload]["variant"] == "V8":
         run_mathblations(a)
+    elif WORKLOADS[a.workload]["variant"] == "VE":
+        run_value_embeds(a)
     else:
         run_ours(a)
