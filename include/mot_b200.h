@@ -140,12 +140,16 @@ int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_t ws_bytes,
 int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                   const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream);
 
-/* The same forward that also keeps rstd_out[n_tokens] (fp32, device): the reciprocal rms of every mixed row, i.e.
- * what F.rms_norm's autograd node saves (spt/train_gpt.py:172-173).  Written when MOT_F_OUT_NORM is set; NULL = not
- * kept.  Together with `out` it lets mot_embed_bwd_saved skip rebuilding the mixed row. */
-int mot_embed_fwd_save(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
-                       const void* E_tok, const void* E_byte, const float* lam, void* out, float* rstd_out,
-                       void* stream);
+/* Extended forward.
+ *   rstd_out : optional fp32 [n_tokens]; receives the reciprocal rms of every mixed row when MOT_F_OUT_NORM is set,
+ *              i.e. what F.rms_norm's autograd node keeps (spt/train_gpt.py:172-173); with `out` it lets
+ *              mot_embed_bwd_ex skip rebuilding the mixed row.
+ *   addend   : optional dense [n_tokens, out_dim] rows (table dtype) added to the mixed row before the output norm:
+ *              z = combine(...) + addend.  With MOT_TOK_ONLY this is `norm(token_embs + F.linear(byte_embs, byte_fc))`
+ *              of runs/71051:226-229 (the product comes from mot_linear_fwd).  Not with split concat / strided rows. */
+int mot_embed_fwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                     const void* E_tok, const void* E_byte, const float* lam, const void* addend, void* out,
+                     float* rstd_out, void* stream);
 
 /* Sort plan for the backward (token ids only; reusable by every table gathered with `tok`). */
 int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* workspace, size_t ws_bytes, int32_t ws_flags,
@@ -169,17 +173,21 @@ int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, co
                   void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                   int32_t ws_flags, void* stream);
 
-/* mot_embed_bwd with the forward's result kept (out_saved = the `out` of mot_embed_fwd_save, rstd_saved = its
- * rstd_out; both NULL = plain mot_embed_bwd).  For the MoT-sum variant (MOT_ADD + MOT_F_OUT_NORM only, runs/71) the
- * backward then reads two rows per occurrence (grad_out and out, same position) instead of the token row plus bpt byte
- * rows: dz = rstd*g - out*(rstd*mean(g.out)).  Other variants ignore the two pointers.  Same results within the
- * rounding of `out` (bf16: one extra 2^-9 relative rounding inside the second term). */
-int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
-                        const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
-                        const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte, float* g_lam,
-                        void* workspace, size_t ws_bytes, int32_t ws_flags, void* stream);
+/* Extended backward.
+ *   out_saved / rstd_saved : the `out` and `rstd_out` of mot_embed_fwd_ex (both NULL = rebuild the mixed row).  For the
+ *       MoT-sum variant (MOT_ADD + MOT_F_OUT_NORM only, runs/71) the backward then reads two rows per occurrence
+ *       (grad_out and out, same position) instead of the token row plus bpt byte rows:
+ *       dz = rstd*g - out*(rstd*mean(g.out)).  Other variants ignore them.  Same results within the rounding of `out`
+ *       (bf16: one extra 2^-9 relative rounding inside the second term).
+ *   addend / d_addend : the dense rows of mot_embed_fwd_ex and the buffer [n_tokens, out_dim] that receives their
+ *       gradient d z (table dtype), which the caller feeds to mot_linear_bwd_* (runs/71051). */
+int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                     const void* E_tok, const void* E_byte, const float* lam, const void* addend,
+                     const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
+                     void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes, int32_t ws_flags,
+                     void* stream);
 
-/* 1 when mot_embed_bwd_saved would use out_saved / rstd_saved for this descriptor (so a caller knows whether keeping
+/* 1 when mot_embed_bwd_ex would use out_saved / rstd_saved for this descriptor (so a caller knows whether keeping
  * them pays), else 0: only the MoT-sum variant, widths 512 / 768 / 1024, and at most 4 positions per vocabulary row
  * (beyond that the token rows of the recompute kernel are L2 hits and it is the faster one). */
 int mot_embed_bwd_uses_saved(const MotDesc* d);

@@ -259,13 +259,15 @@ extern "C" size_t mot_embed_workspace_bytes(const MotDesc* d) {
 
 extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
                              const void* E_tok, const void* E_byte, const float* lam, void* out, void* stream) {
-  return mot_embed_fwd_save(d, tok, byte_ids, ttb, E_tok, E_byte, lam, out, nullptr, stream);
+  return mot_embed_fwd_ex(d, tok, byte_ids, ttb, E_tok, E_byte, lam, nullptr, out, nullptr, stream);
 }
 
-extern "C" int mot_embed_fwd_save(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
-                                  const void* E_tok, const void* E_byte, const float* lam, void* out, float* rstd_out,
-                                  void* stream) {
+extern "C" int mot_embed_fwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                const void* E_tok, const void* E_byte, const float* lam, const void* addend, void* out,
+                                float* rstd_out, void* stream) {
   if (int rc = validate(d)) return rc;
+  if (addend && (concat_splits(d) || d->row_stride != 0 || d->col_offset != 0)) return MOT_ERR_UNSUPPORTED;
+  if (!aligned16(addend)) return MOT_ERR_MISALIGNED;
   if (d->n_tokens == 0) return MOT_OK;  // empty batch: nothing to write (empty tensors have null pointers)
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
   if (!out || (has_tok && (!tok || !E_tok)) || (has_bytes && !E_byte)) return MOT_ERR_BAD_ARG;
@@ -289,6 +291,8 @@ extern "C" int mot_embed_fwd_save(const MotDesc* d, const int32_t* tok, const vo
   fill_params(d, p);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam; p.out = out;
   p.rstd_out = (d->flags & MOT_F_OUT_NORM) ? rstd_out : nullptr;
+  p.addend = addend;
+  if (addend) return d->dtype == MOT_BF16 ? dispatch_fwd_addend_bf16(p, s) : dispatch_fwd_addend_f32(p, s);
   return d->dtype == MOT_BF16 ? dispatch_fwd_bf16(p, s) : dispatch_fwd_f32(p, s);
 }
 
@@ -341,7 +345,7 @@ extern "C" int mot_stream_wait_event(void* stream, void* event) {
   return MOT_OK;
 }
 
-// Would mot_embed_bwd_saved run the saved-output kernel for this descriptor?  (variant, width with an instantiation,
+// Would mot_embed_bwd_ex run the saved-output kernel for this descriptor?  (variant, width with an instantiation,
 // and few enough positions per vocabulary row, see below)
 static bool saved_path_applies(const MotDesc* d, const EmbedParams& p) {
   static const bool no_saved = getenv("MOT_NO_SAVED_BWD") != nullptr;  // debug knob (A/B timing)
@@ -365,19 +369,23 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
                              const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
                              void* gE_tok, void* gE_byte, float* g_lam, void* workspace, size_t ws_bytes,
                              int32_t ws_flags, void* stream) {
-  return mot_embed_bwd_saved(d, tok, byte_ids, ttb, E_tok, E_byte, lam, grad_out, nullptr, nullptr, gE_tok, gE_byte, g_lam,
-                             workspace, ws_bytes, ws_flags, stream);
+  return mot_embed_bwd_ex(d, tok, byte_ids, ttb, E_tok, E_byte, lam, nullptr, grad_out, nullptr, nullptr, gE_tok, gE_byte,
+                          g_lam, nullptr, workspace, ws_bytes, ws_flags, stream);
 }
 
-extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
-                                   const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
-                                   const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte,
-                                   float* g_lam, void* workspace, size_t ws_bytes, int32_t ws_flags, void* stream) {
+extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                const void* E_tok, const void* E_byte, const float* lam, const void* addend,
+                                const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
+                                void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes,
+                                int32_t ws_flags, void* stream) {
   const bool plan_ready = (ws_flags & MOT_WS_PLAN_READY) != 0, ws_clean = (ws_flags & MOT_WS_CLEAN) != 0;
   if (int rc = validate(d)) return rc;
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
   if (has_tok && !gE_tok) return MOT_ERR_BAD_ARG;
   if (has_bytes && !gE_byte) return MOT_ERR_BAD_ARG;
+  if ((addend || d_addend) && (concat_splits(d) || d->row_stride != 0 || d->col_offset != 0)) return MOT_ERR_UNSUPPORTED;
+  if (d_addend && (d->flags & MOT_F_OUT_NORM) && !addend) return MOT_ERR_BAD_ARG;  // d z needs z: the addend itself
+  if (!aligned16(addend) || !aligned16(d_addend)) return MOT_ERR_MISALIGNED;
   if (!aligned16(gE_tok) || !aligned16(gE_byte)) return MOT_ERR_MISALIGNED;
   if (d->n_tokens == 0) {  // nothing gathered: dense zero grads
     cudaStream_t s0 = reinterpret_cast<cudaStream_t>(stream);
@@ -405,6 +413,7 @@ extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const v
   bind_ws(p, w, workspace);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam;
   p.gout = grad_out; p.gE_tok = gE_tok; p.gE_byte = gE_byte; p.g_lam = g_lam;
+  p.addend = addend; p.d_addend = d_addend;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
   if (!plan_ready) {
@@ -429,7 +438,7 @@ extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const v
     // the MoT-sum variant with the forward result kept: the saved-output kernel (mot_embed_bwd_sum.cuh); every other
     // case recomputes the mixed row
     rc = -1;
-    if (out_saved && rstd_saved && saved_path_applies(d, p)) {
+    if (out_saved && rstd_saved && !addend && !d_addend && saved_path_applies(d, p)) {
       if (!aligned16(out_saved)) return MOT_ERR_MISALIGNED;
       p.out_saved = out_saved;
       p.rstd = rstd_saved;
@@ -438,6 +447,7 @@ extern "C" int mot_embed_bwd_saved(const MotDesc* d, const int32_t* tok, const v
       rc = d->dtype == MOT_BF16 ? dispatch_bwd_sum_bf16(p, s) : dispatch_bwd_sum_f32(p, s);
       if (rc < 0) p.R = r_default;
     }
+    if (rc < 0 && (addend || d_addend)) rc = d->dtype == MOT_BF16 ? dispatch_bwd_addend_bf16(p, s) : dispatch_bwd_addend_f32(p, s);
     if (rc < 0) rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
   }
   if (rc) return rc;

@@ -47,8 +47,10 @@ struct EmbedParams {
   float* rstd_out;  // optional [N]: reciprocal rms of every mixed row (out_norm), kept for the saved-output backward
   // backward
   const void* gout;
-  const void* out_saved;  // optional: the forward result and its rstd (mot_embed_bwd_saved)
+  const void* out_saved;  // optional: the forward result and its rstd (mot_embed_bwd_ex)
   const float* rstd;
+  const void* addend;     // optional dense [N, Do] rows added to the mixed row before the output norm (runs/71051:228-229)
+  void* d_addend;         // backward: receives d(mixed row) [N, Do], the gradient of `addend`
   void* gE_tok;
   void* gE_byte;
   float* g_lam;
@@ -171,22 +173,27 @@ __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s,
 
 // Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all variants);
 // MODE 1: the MoT-sum fast path (runs/71): combine == ADD, out_norm only, no lambdas;
+// MODE 4: MODE 0 plus a dense [N, Do] addend to the mixed row and its gradient (runs/71051:226-229);
 // MODE 2 / 3: the two halves of the split [tok | bytes] concat operand of the projection variants (runs/7:226-232):
 //   2 = tok-only rows with the per-input token norm, 3 = bytes-only rows with the per-byte norm (neither has a norm
 //   over the mixed row, so the backward needs no reduction and keeps nothing of the row in registers).
+// MODE 0 and MODE 4 decide every variant flag at run time; MODE 4 additionally handles the dense addend (kept out of
+// MODE 0 so that the common kernels do not carry its registers)
+#define MOT_RT(M) ((M) == 0 || (M) == 4)
 template <int MODE>
 struct Cfg {
-  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 2 || (MODE == 0 && (p.flags & MOT_F_TOK_NORM)); }
+  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 2 || (MOT_RT(MODE) && (p.flags & MOT_F_TOK_NORM)); }
   __device__ __forceinline__ static bool byte_scale(const EmbedParams& p) {
-    return MODE == 3 || (MODE == 0 && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN));
+    return MODE == 3 || (MOT_RT(MODE) && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN));
   }
-  __device__ __forceinline__ static bool has_lam(const EmbedParams& p) { return MODE == 0 && (p.flags & MOT_F_HAS_LAMBDAS); }
-  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (MODE == 0 && (p.flags & MOT_F_OUT_NORM)); }
-  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || MODE == 2 || (MODE == 0 && p.combine != MOT_BYTES_ONLY); }
-  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || MODE == 3 || (MODE == 0 && p.combine != MOT_TOK_ONLY); }
-  __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MODE == 0 && p.combine == MOT_MEAN; }
+  __device__ __forceinline__ static bool has_lam(const EmbedParams& p) { return MOT_RT(MODE) && (p.flags & MOT_F_HAS_LAMBDAS); }
+  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (MOT_RT(MODE) && (p.flags & MOT_F_OUT_NORM)); }
+  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || MODE == 2 || (MOT_RT(MODE) && p.combine != MOT_BYTES_ONLY); }
+  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || MODE == 3 || (MOT_RT(MODE) && p.combine != MOT_TOK_ONLY); }
+  __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MOT_RT(MODE) && p.combine == MOT_MEAN; }
 };
 inline int pick_mode(const EmbedParams& p, int cw) {
+  if (p.addend != nullptr || p.d_addend != nullptr) return 4;  // the dense addend has its own instantiations
   const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
   if (p.Do % (32 * cw) != 0) return 0;
   if (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.tab_smem) return 1;
@@ -195,11 +202,11 @@ inline int pick_mode(const EmbedParams& p, int cw) {
   return 0;
 }
 
-#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || (MODE == 0 && cm[it].toff >= 0))
-#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || (MODE == 0 && cm[it].slot >= 0))
+#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || (MOT_RT(MODE) && cm[it].toff >= 0))
+#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || (MOT_RT(MODE) && cm[it].slot >= 0))
 // element offset of chunk `it` in the token row: affine (base + immediate addressing) on the fast path
 #define MOT_TOFF(it) ((MODE == 1 || MODE == 2) ? ((it) * 32 + lane) * CW : cm[it].toff)
-#define MOT_CHUNK_OK(it) (MODE != 0 || ((it) * 32 + lane) * CW < p.Do)
+#define MOT_CHUNK_OK(it) (!MOT_RT(MODE) || ((it) * 32 + lane) * CW < p.Do)
 
 template <typename T, int MODE = 0, int CW = 8>
 __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     float ss = 0.f;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
-      if (MODE == 0) {
+      if (MOT_RT(MODE)) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[it][e] *= tscale;
       }
@@ -420,6 +427,12 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
             }
           }
         }
+      }
+      if (MODE == 4 && p.addend != nullptr && MOT_CHUNK_OK(it)) {
+        float ad[8];
+        Vec8<T>::unpack(Vec8<T>::ldg_raw(reinterpret_cast<const T*>(p.addend) + (size_t)pos * p.Do + (size_t)(it * 32 + lane) * kChunk), ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[it][e] += ad[e];
       }
       if (out_norm) {
 #pragma unroll
@@ -505,7 +518,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
         V::unpack(V::lds_raw(trow_smem + MOT_TOFF(it)), tv);
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e] - b * tv[e];
-      } else if (MODE == 0) {
+      } else if (MOT_RT(MODE)) {
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e];
       } else {
@@ -712,6 +725,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
     int id_next = id_lane ? load_raw_id(p, idsrc, pos_first, lane) : 0;
     for (int k = 0; k < A.cnt; ++k) {
       const int v = __shfl_sync(0xffffffffu, A.v, k);
+      const int pos_k = __shfl_sync(0xffffffffu, A.pos, k);  // position of this occurrence (dense addend rows)
       const bool new_row = has_tok && v != cur_v;
       if (new_row) {  // flush BEFORE refilling the ring: the old row's token row sits in stage (consumed-1) % D
         if (cur_v >= 0) flush(false);
@@ -759,7 +773,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       for (int it = 0; it < CPL; ++it) {
         if (has_tok && MOT_TOK_OK(it)) {
           V::unpack(V::lds_raw(trow + MOT_TOFF(it)), z[it]);
-          if (MODE == 0) {
+          if (MOT_RT(MODE)) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) z[it][e] *= tscale;
           }
@@ -795,6 +809,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
             }
           }
         }
+        if (MODE == 4 && p.addend != nullptr && MOT_CHUNK_OK(it)) {
+          float ad[CW];
+          V::unpack(V::ldg_raw(reinterpret_cast<const T*>(p.addend) + (size_t)pos_k * p.Do + (size_t)(it * 32 + lane) * CW), ad);
+#pragma unroll
+          for (int e = 0; e < CW; ++e) z[it][e] += ad[e];
+        }
         if (MOT_CHUNK_OK(it)) {
           V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), gr[it]);
 #pragma unroll
@@ -829,6 +849,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
             for (int e = 0; e < CW; ++e) Du[it][e] += dz[e];
           }
+          if (MODE == 4 && p.d_addend != nullptr)
+            V::stg(reinterpret_cast<T*>(p.d_addend) + (size_t)pos_k * p.Do + (size_t)(it * 32 + lane) * CW, dz);
         } else {
 #pragma unroll
           for (int e = 0; e < CW; ++e) dz[e] = 0.f;
@@ -860,7 +882,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
               for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
             }
-            if (MODE == 0) {
+            if (MOT_RT(MODE)) {
 #pragma unroll
               for (int e = 0; e < CW; ++e) dz[e] *= lam_b_eff;
             }
@@ -1113,6 +1135,10 @@ int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
 int dispatch_bwd_sum_bf16(const EmbedParams& p, cudaStream_t s);  // saved-output MoT-sum kernel; -1: not applicable
 int dispatch_bwd_sum_f32(const EmbedParams& p, cudaStream_t s);
+int dispatch_fwd_addend_bf16(const EmbedParams& p, cudaStream_t s);  // MODE 4 instantiations
+int dispatch_fwd_addend_f32(const EmbedParams& p, cudaStream_t s);
+int dispatch_bwd_addend_bf16(const EmbedParams& p, cudaStream_t s);
+int dispatch_bwd_addend_f32(const EmbedParams& p, cudaStream_t s);
 int launch_finalize_bf16(const EmbedParams& p, int blocks, cudaStream_t s);
 int launch_finalize_f32(const EmbedParams& p, int blocks, cudaStream_t s);
 

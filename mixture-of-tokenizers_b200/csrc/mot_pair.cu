@@ -61,7 +61,7 @@ __device__ __forceinline__ float group_sum(float v) {
 
 // MAXJ = 8-element chunks per lane (ceil(bd / 8 / G))
 template <typename T, int G, int MAXJ>
-__global__ void __launch_bounds__(kPairThreads, 2) mot_pair_fwd_kernel(const PairParams p) {
+__global__ void __launch_bounds__(kPairThreads, MAXJ <= 4 ? 2 : 1) mot_pair_fwd_kernel(const PairParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t tab_bar;
   T* tab = reinterpret_cast<T*>(smem_raw);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) mot_pair_fwd_kernel(const Pai
 // receive ds (fp32 RED.v4 into one of n_rep L2-resident replicas; mot_bwd_finalize_kernel sums and casts them).
 // Two passes over the slot (reduce, then scatter) so that nothing of the row is held across the reduction.
 template <typename T, int G, int MAXJ>
-__global__ void __launch_bounds__(kPairThreads, 2) mot_pair_bwd_kernel(const PairParams p) {
+__global__ void __launch_bounds__(kPairThreads, MAXJ <= 4 ? 2 : 1) mot_pair_bwd_kernel(const PairParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t tab_bar;
   T* tab = reinterpret_cast<T*>(smem_raw);
@@ -192,7 +192,7 @@ static int launch_pair(const PairParams& p, bool backward, cudaStream_t s) {
   const size_t smem = align_up((size_t)p.Vb * p.bd * sizeof(T), 128);
   if (smem + 1024 > (size_t)optin) return MOT_ERR_UNSUPPORTED;  // table does not fit in shared memory
   long long blocks = (p.N + kPairThreads / 32 - 1) / (kPairThreads / 32);
-  const int per_sm = 2 * (smem + 1024) <= (size_t)optin ? 2 : 1;  // two CTAs per SM while two tables fit
+  const int per_sm = (MAXJ <= 4 && 2 * (smem + 1024) <= (size_t)optin) ? 2 : 1;  // two CTAs per SM while two tables fit
   if (blocks > (long long)per_sm * sms) blocks = (long long)per_sm * sms;
   if (blocks < 1) blocks = 1;
   if (backward) {

@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .ops import MixSpec, mot_embed, mot_embed_proj, tok_gather
+from .ops import MixSpec, mot_embed, mot_embed_byte_fc, mot_embed_proj, tok_gather
 
 # variant name -> MixSpec kwargs (`slot_major` is the `.view(bpt,-1)` id layout of the sum runs)
 RUN_VARIANTS = {
@@ -120,6 +120,27 @@ class MoTProjEmbedding(nn.Module):
         assert token_inputs.ndim == 1  # runs/7:305
         x = mot_embed_proj(token_inputs, byte_inputs, self.embed_tokens.weight, self.embed_bytes.weight,
                            self.byte_mixin_weight, self.spec, bpt=self.bpt)
+        return x[None]
+
+
+class MoTByteFcEmbedding(nn.Module):
+    """runs/71051:226-229,253,312-314 (V3f): parameters `embed_tokens.weight`, `embed_bytes.weight`, `byte_fc`
+    [model_dim, model_dim] bf16; forward(token_inputs [T], byte_inputs [bpt, T]) ->
+    norm(embed_tokens(tok) + F.linear(cat(embed_bytes(bytes)), byte_fc)) as [1, T, model_dim]."""
+
+    def __init__(self, token_vocab_size: int, byte_vocab_size: int, model_dim: int, byte_dim: int, bytes_per_token: int = 16):
+        super().__init__()
+        if byte_dim * bytes_per_token != model_dim:
+            raise ValueError("MoTByteFcEmbedding: bytes_per_token * byte_dim must equal model_dim (runs/71051:500-501)")
+        self.bpt = bytes_per_token
+        self.embed_tokens = nn.Embedding(token_vocab_size, model_dim)
+        self.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim)
+        self.byte_fc = nn.Parameter(_init_linear_(torch.empty(model_dim, model_dim)).bfloat16())
+
+    def forward(self, token_inputs: torch.Tensor, byte_inputs: torch.Tensor) -> torch.Tensor:
+        assert token_inputs.ndim == 1
+        x = mot_embed_byte_fc(token_inputs, byte_inputs, self.embed_tokens.weight, self.embed_bytes.weight, self.byte_fc,
+                              bpt=self.bpt)
         return x[None]
 
 

@@ -182,22 +182,23 @@ def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Opt
 
 
 def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None,
-                      rstd: Optional[torch.Tensor] = None) -> None:
+                      rstd: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None) -> None:
     """mot_embed_fwd on caller-allocated tensors (no allocation, no sync; CUDA-graph capturable).  `rstd` (fp32
-    [n_tokens]) additionally keeps the reciprocal rms of every mixed row for the saved-output backward."""
+    [n_tokens]) additionally keeps the reciprocal rms of every mixed row for the saved-output backward; `addend`
+    ([n_tokens, out_dim]) is added to the mixed row before the output norm (mot_embed_fwd_ex)."""
     dev = out.device
     with _on_device(dev):
-        if rstd is None:
+        if rstd is None and addend is None:
             rc = L.lib().mot_embed_fwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
                                        _ptr(out), _stream(dev) if stream is None else stream)
         else:
-            rc = L.lib().mot_embed_fwd_save(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
-                                            _ptr(out), _ptr(rstd), _stream(dev) if stream is None else stream)
+            rc = L.lib().mot_embed_fwd_ex(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                          _ptr(addend), _ptr(out), _ptr(rstd), _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_fwd")
 
 
 def embed_bwd_uses_saved(desc: L.MotDesc) -> bool:
-    """Whether mot_embed_bwd_saved would read the kept forward result for this descriptor (MoT-sum, moderate N)."""
+    """Whether mot_embed_bwd_ex would read the kept forward result for this descriptor (MoT-sum, moderate N)."""
     return bool(L.lib().mot_embed_bwd_uses_saved(desc))
 
 
@@ -222,22 +223,23 @@ def embed_plan(desc: L.MotDesc, tok, ws, ws_clean: bool = False) -> None:
 
 def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
                        plan_ready: bool = False, ws_clean: bool = False, stream: Optional[int] = None,
-                       out_saved: Optional[torch.Tensor] = None, rstd: Optional[torch.Tensor] = None) -> None:
+                       out_saved: Optional[torch.Tensor] = None, rstd: Optional[torch.Tensor] = None,
+                       addend: Optional[torch.Tensor] = None, d_addend: Optional[torch.Tensor] = None) -> None:
     """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten.  `ws_clean`: the caller
     vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward).
-    `out_saved` + `rstd` (what embed_forward_out(..., rstd=) produced): mot_embed_bwd_saved."""
+    `out_saved` + `rstd` (what embed_forward_out(..., rstd=) produced) and `addend` / `d_addend`: mot_embed_bwd_ex."""
     dev = grad_out.device
     flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0)
     with _on_device(dev):
-        if out_saved is None or rstd is None:
+        if (out_saved is None or rstd is None) and addend is None and d_addend is None:
             rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
                                        _ptr(grad_out), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam), _ptr(ws), ws.numel(),
                                        flags, _stream(dev) if stream is None else stream)
         else:
-            rc = L.lib().mot_embed_bwd_saved(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
-                                             _ptr(grad_out), _ptr(out_saved), _ptr(rstd), _ptr(gE_tok), _ptr(gE_byte),
-                                             _ptr(g_lam), _ptr(ws), ws.numel(), flags,
-                                             _stream(dev) if stream is None else stream)
+            rc = L.lib().mot_embed_bwd_ex(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                          _ptr(addend), _ptr(grad_out), _ptr(out_saved), _ptr(rstd), _ptr(gE_tok),
+                                          _ptr(gE_byte), _ptr(g_lam), _ptr(d_addend), _ptr(ws), ws.numel(), flags,
+                                          _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_bwd")
 
 
@@ -353,7 +355,7 @@ class _MotEmbedFn(torch.autograd.Function):
             ctx.ws = acquire_workspace(desc, dev)
             embed_plan_async(desc, tok, ctx.ws, dev, st)
         # MoT-sum (runs/71): keep what rms_norm's autograd node keeps (its result and rstd); the backward then reads two
-        # rows per occurrence instead of rebuilding the mixed row (mot_embed_bwd_saved)
+        # rows per occurrence instead of rebuilding the mixed row (mot_embed_bwd_ex)
         keep = needs_grad and n > 0 and bool(L.lib().mot_embed_bwd_uses_saved(desc))
         rstd = torch.empty(n, dtype=torch.float32, device=dev) if keep else None
         embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st, rstd=rstd)
@@ -699,6 +701,94 @@ class _MotEmbedProjFn(torch.autograd.Function):
         gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
         return (None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None),
                 None)
+
+
+class _MotEmbedByteFcFn(torch.autograd.Function):
+    """runs/71051:226-229,312-314 (V3f): out = norm(embed_tokens(tok) + F.linear(cat_k embed_bytes(ids_k), byte_fc)).
+    Forward: bytes-only gather of the [n, D] operand (ids in the `.view(bpt,-1)` order), tcgen05 product, then the fused
+    token gather + add + rms-norm (mot_embed_fwd_ex with the product as dense addend).  Backward: the fused kernel
+    scatters d z into the token table and writes it densely as the gradient of the product; dW, dX on the tensor
+    cores; bytes-only scatter.  The operand is gathered again in the backward, not kept."""
+
+    @staticmethod
+    def forward(ctx, spec_b: MixSpec, bpt: int, eps: float, tokens, byte_ids, E_tok, E_byte, W):
+        dev = _require_cuda(tokens, byte_ids, E_tok, E_byte, W)
+        cdt = E_tok.dtype
+        if cdt not in (torch.bfloat16, torch.float32) or E_byte.dtype != cdt:
+            raise NotImplementedError("mot_b200: token and byte tables must both be bf16 or both fp32")
+        tok = tokens.reshape(-1)
+        tok = (tok if tok.dtype == torch.int32 else tok.to(torch.int32)).contiguous()
+        if byte_ids.dtype not in (torch.int32, torch.int64):
+            raise NotImplementedError("mot_b200: byte ids must be int32 or int64")
+        ids = byte_ids.contiguous()
+        n = tok.numel()
+        E_tok_c, E_byte_c = E_tok.contiguous(), E_byte.contiguous()
+        D = E_tok_c.shape[1]
+        if ids.numel() != n * bpt or bpt * E_byte_c.shape[1] != D or tuple(W.shape) != (D, D):
+            raise RuntimeError("mot_b200: byte-FC mix needs bpt*byte_dim == token_dim and a square [D, D] weight")
+        w16 = W.detach().to(cdt).contiguous()
+        desc_b = make_desc(spec_b, n, None, E_byte_c, bpt, ids=ids, ttb=None, has_lam=False)
+        desc_t = make_desc(MixSpec(combine="tok_only", out_norm=True, eps=eps), n, E_tok_c, None, 0, ids=None, ttb=None,
+                           has_lam=False)
+        ctx.ws = None
+        if ctx.needs_input_grad[5] and n > 0:
+            ctx.ws = acquire_workspace(desc_t, dev)
+            embed_plan_async(desc_t, tok, ctx.ws, dev)
+        C = torch.empty((n, D), dtype=cdt, device=dev)
+        embed_forward_out(desc_b, None, ids, None, None, E_byte_c, None, C)
+        Y = torch.empty((n, D), dtype=cdt, device=dev)
+        linear_forward_out(C, w16, Y)
+        del C
+        out = torch.empty((n, D), dtype=cdt, device=dev)
+        if n > 0:
+            embed_forward_out(desc_t, tok, None, None, E_tok_c, None, None, out, addend=Y)
+        ctx.desc_b, ctx.desc_t, ctx.dev, ctx.w_dtype = desc_b, desc_t, dev, W.dtype
+        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tok, ids, E_tok, E_byte, w16, Y = ctx.saved_tensors
+        desc_b, desc_t, dev = ctx.desc_b, ctx.desc_t, ctx.dev
+        n, D = Y.shape
+        cdt = Y.dtype
+        g = grad_out.reshape(n, D).to(cdt).contiguous()
+        gE_tok, gE_byte = torch.empty_like(E_tok), torch.empty_like(E_byte)
+        dY = torch.empty_like(Y)
+        ws, planned = ctx.ws, ctx.ws is not None
+        if ws is None:
+            ws = acquire_workspace(desc_t, dev)
+        if planned:
+            embed_plan_join(ws, dev)
+            clean = True
+        else:
+            clean, ws.clean = ws.clean, False
+        embed_backward_out(desc_t, tok, None, None, E_tok, None, None, g, gE_tok, None, None, ws.buf,
+                           plan_ready=planned, ws_clean=clean, addend=Y, d_addend=dY)
+        ws.clean = True
+        ctx.ws = None
+        release_workspace(ws)
+        C = torch.empty((n, D), dtype=cdt, device=dev)
+        embed_forward_out(desc_b, None, ids, None, None, E_byte, None, C)            # gathered again, not kept
+        dW32 = torch.empty((D, D), dtype=torch.float32, device=dev)
+        dW16 = torch.empty((D, D), dtype=torch.bfloat16, device=dev) if ctx.w_dtype == torch.bfloat16 else None
+        linear_bwd_weight_out(dY, C, dW32, dW16)
+        linear_bwd_input_out(dY, w16, C)                                             # dC overwrites the operand buffer
+        wsb = acquire_workspace(desc_b, dev)
+        clean_b, wsb.clean = wsb.clean, False
+        embed_backward_out(desc_b, None, ids, None, None, E_byte, None, C, None, gE_byte, None, wsb.buf,
+                           plan_ready=False, ws_clean=clean_b)
+        wsb.clean = True
+        release_workspace(wsb)
+        gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
+        return None, None, None, None, None, gE_tok, gE_byte, gW
+
+
+def mot_embed_byte_fc(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Tensor, E_byte: torch.Tensor,
+                      W_fc: torch.Tensor, *, bpt: int = 16, slot_major: bool = True, eps: float = FP32_EPS) -> torch.Tensor:
+    """`norm(token_embs + F.linear(cat(byte_embs), byte_fc))` (runs/71051:226-229,312-314): [n_tokens, D]."""
+    spec_b = MixSpec(combine="bytes_only", out_norm=False, slot_major=slot_major, eps=eps)
+    return _MotEmbedByteFcFn.apply(spec_b, bpt, eps, tokens, byte_ids, E_tok, E_byte, W_fc)
 
 
 def mot_embed_proj(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Tensor, E_byte: torch.Tensor,

@@ -125,6 +125,8 @@ def test_value_embedding_modules_keep_reference_names_and_refuse_cpu():
     assert names[3:6] == [f"value_embeds_bytes.{i}.weight" for i in range(3)]
     assert names[6:] == [f"value_byte_mixin_weights.{i}" for i in range(3)]
     assert tuple(m9.value_byte_mixin_weights[0].shape) == (64, 64 + 16 * 16) and m9.value_byte_mixin_weights[0].dtype == torch.bfloat16
+    m51 = mot_b200.MoTByteFcEmbedding(1000, 458, 512, 32, 16)                                         # runs/71051:253
+    assert tuple(m51.byte_fc.shape) == (512, 512) and m51.byte_fc.dtype == torch.bfloat16
     m81 = mot_b200.MoTSplitResidualEmbedding(1000, 458, 512, 32, 16)                                  # runs/71081
     assert [n for n, _ in m81.named_parameters()] == ["lambdas", "embed_tokens.weight", "embed_bytes.weight"]
     with pytest.raises(ValueError):

@@ -257,7 +257,7 @@ def test_full_size_properties():
     (torch.bfloat16, 512, 64, 8, 1, 10, False),
 ])
 def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V, zipf):
-    """mot_embed_bwd_saved (reads grad_out + the kept forward result, mot_embed_bwd_sum.cuh) against mot_embed_bwd
+    """mot_embed_bwd_ex (reads grad_out + the kept forward result, mot_embed_bwd_sum.cuh) against mot_embed_bwd
     (rebuilds the mixed row) and against the oracle, through the C ABI on caller-allocated tensors."""
     import mot_b200
     from mot_b200 import ops

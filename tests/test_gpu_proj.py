@@ -246,6 +246,46 @@ def test_spt_add_padded_and_pulled_matches_reference_golden_and_oracle(golden_di
     assert nerr(m.byte_mixin.mixin.mixin.weight.grad, want["W"]) <= TOL_CHAIN
 
 
+def test_byte_fc_variant_matches_reference_golden_and_oracle(golden_dir):
+    """V3f (runs/71051:226-229,312-314): norm(tok + F.linear(cat(bytes), byte_fc)) through MoTByteFcEmbedding: the
+    reference's own bf16 / fp32 outputs and gradients at toy size, then the shipped 1024 = 16 x 64 shape vs the oracle."""
+    import mot_b200
+    d = dev()
+    g = np.load(os.path.join(golden_dir, "runs_float.npz"))
+    for tag, dtype, tol in (("V3f_run71051_bf16", torch.bfloat16, TOL_CHAIN), ("V3f_run71051_f32", torch.float32, TOL_TF32_CHAIN)):
+        V, Dm = g[f"{tag}_E_tok"].shape
+        bd = g[f"{tag}_E_byte"].shape[1]
+        m = mot_b200.MoTByteFcEmbedding(V, 458, Dm, bd, Dm // bd).to(d)
+        assert sorted(n for n, _ in m.named_parameters()) == ["byte_fc", "embed_bytes.weight", "embed_tokens.weight"]
+        m = m.to(dtype)
+        with torch.no_grad():
+            m.embed_tokens.weight.copy_(torch.from_numpy(g[f"{tag}_E_tok"]))
+            m.embed_bytes.weight.copy_(torch.from_numpy(g[f"{tag}_E_byte"]))
+            m.byte_fc.copy_(torch.from_numpy(g[f"{tag}_W"]))
+        out = m(torch.from_numpy(g[f"{tag}_tokens"]).to(d), torch.from_numpy(g[f"{tag}_byte_inputs"]).to(d))
+        out.backward(torch.from_numpy(g[f"{tag}_gout"]).to(d).to(dtype).reshape(out.shape))
+        assert nerr(out, torch.from_numpy(g[f"{tag}_out"]).reshape(out.shape)) <= tol
+        assert nerr(m.embed_tokens.weight.grad, torch.from_numpy(g[f"{tag}_gE_tok"])) <= tol
+        assert nerr(m.embed_bytes.weight.grad, torch.from_numpy(g[f"{tag}_gE_byte"])) <= tol
+        assert nerr(m.byte_fc.grad, torch.from_numpy(g[f"{tag}_gW"])) <= tol
+
+    gen = torch.Generator().manual_seed(23)
+    V, Vb, bpt, bd, N = 3000, 458, 16, 64, 2500
+    Dm = bpt * bd
+    m = mot_b200.MoTByteFcEmbedding(V, Vb, Dm, bd, bpt).to(d).bfloat16()
+    toks = (torch.rand(N, generator=gen) ** 3 * V).long().clamp_(0, V - 1).int()      # hot rows straddle stream chunks
+    ids = torch.randint(0, Vb, (bpt, N), generator=gen, dtype=torch.int32)
+    gout = torch.randn(1, N, Dm, generator=gen).bfloat16()
+    out = m(toks.to(d), ids.to(d))
+    out.backward(gout.to(d))
+    Et, Eb, W = (t.detach().cpu() for t in (m.embed_tokens.weight, m.embed_bytes.weight, m.byte_fc))
+    want_out, want = O.mot_embed_fwd_bwd(O.VARIANTS["V3f"][0], toks, ids, Et, Eb, gout, bpt=bpt, slot_major=True, W=W)
+    assert nerr(out[0], want_out) <= TOL_CHAIN
+    assert nerr(m.embed_tokens.weight.grad, want["E_tok"]) <= TOL_CHAIN
+    assert nerr(m.embed_bytes.weight.grad, want["E_byte"]) <= TOL_CHAIN
+    assert nerr(m.byte_fc.grad, want["W"]) <= TOL_CHAIN
+
+
 def test_spt_module_refuses_unsupported_options():
     import mot_b200
     for kw in (dict(byte_mixin_method="cross_attn"), dict(use_byte_self_attn=True)):
