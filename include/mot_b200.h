@@ -112,6 +112,10 @@ void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* 
 int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
                    int32_t ttb_dtype, void* out, int32_t out_i64, void* stream);
 
+/* uint16 shard tokens -> int32 ids on the device.  Replaces the host-side `.to(torch.int32)` of load_data_shard
+ * (spt/train_gpt.py:640-648) so that the upload moves the shard's own 2 bytes per token.  Pointers 16-byte aligned. */
+int mot_tokens_widen_u16(const void* tok_u16, int64_t n, int32_t* out, void* stream);
+
 /* tokens -> padded digit ids, the arithmetic ttb analogue of mathblations (GenerateEquations.tokens_to_digits,
  * mathblations/data.py:92-109): decimal digits right-aligned in dpt slots, pad 13; op / eq / pad tokens -> 10 / 11 / 12
  * in the last slot.  tok int32 or int64 (tok_i64), out [n, dpt] int32 or int64 (out_i64). */

@@ -83,7 +83,43 @@ __global__ void __launch_bounds__(256) tokens_to_digits_kernel(const TokT* __res
   }
 }
 
+// Shard tokens are stored as uint16 (spt/train_gpt.py:628-638; modded-nanogpt/data/fineweb.py): widen them to the int32
+// ids every kernel of the path takes, on the device, so that the host -> device copy moves 2 bytes per token instead of
+// the 4 of the reference's host-side `.to(torch.int32)` (spt/train_gpt.py:646).  8 tokens per thread: one 16-byte load,
+// two 16-byte stores; HBM bound at 6 bytes per token.
+__global__ void __launch_bounds__(256) tokens_widen_u16_kernel(const unsigned short* __restrict__ in, long long n, int* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long groups = n >> 3;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint4 r = ldg_nc_16(in + (g << 3));
+    uint4 a, b;
+    a.x = r.x & 0xffffu; a.y = r.x >> 16; a.z = r.y & 0xffffu; a.w = r.y >> 16;
+    b.x = r.z & 0xffffu; b.y = r.z >> 16; b.z = r.w & 0xffffu; b.w = r.w >> 16;
+    stg_16(out + (g << 3), a);
+    stg_16(out + (g << 3) + 4, b);
+  }
+  for (long long i = (groups << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
+}
+
 }  // namespace mot
+
+extern "C" int mot_tokens_widen_u16(const void* tok_u16, int64_t n, int32_t* out, void* stream) {
+  if (n < 0) return MOT_ERR_BAD_ARG;
+  if (n == 0) return MOT_OK;
+  if (!tok_u16 || !out) return MOT_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(tok_u16) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return MOT_ERR_MISALIGNED;
+  int sms = 0, optin = 0;
+  if (int rc = mot::device_props(&sms, &optin)) return rc;
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > sms * 8LL) blocks = sms * 8LL;
+  if (blocks < 1) blocks = 1;
+  mot::launch_pdl(mot::tokens_widen_u16_kernel, dim3((unsigned)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                  reinterpret_cast<const unsigned short*>(tok_u16), (long long)n, out);
+  mot::count_launch();
+  return mot::check_launch();
+}
 
 extern "C" int mot_tokens_to_digits(const void* tok, int64_t n, int32_t tok_i64, int32_t dpt, int64_t op_token, int64_t eq_token,
                                     int64_t pad_token, void* out, int32_t out_i64, void* stream) {

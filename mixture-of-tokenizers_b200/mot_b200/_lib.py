@@ -57,6 +57,7 @@ _SIGNATURES = {
     "mot_embed_fwd_ex": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mot_embed_bwd_ex": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    C.c_size_t, C.c_int32, _P]),
+    "mot_tokens_widen_u16": (C.c_int, [_P, C.c_int64, _P, _P]),
     "mot_embed_bwd_uses_saved": (C.c_int, [C.POINTER(MotDesc)]),
     "mot_byte_pair_fwd": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P,
                                     C.c_int64, C.c_int32, _P]),
