@@ -6,8 +6,12 @@ int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
   const int cpl = (p.Do + 32 * kBwdCW - 1) / (32 * kBwdCW);  // 4-element chunks per lane
   const int mode = pick_mode(p, kBwdCW);
-  if (mode >= 2) {
+  if (mode == 2 || mode == 3) {
     const int rc = dispatch_bwd_split_bf16(p, mode, s);
+    if (rc >= 0) return rc;
+  }
+  if (mode == 5 || mode >= 16) {  // plain gather / ADD family with compile-time flags
+    const int rc = dispatch_bwd_static_bf16(p, mode, s);
     if (rc >= 0) return rc;
   }
   if (mode == 1) {  // MoT-sum fast path (runs/71): 512 = 8 x 64, 768 = 16 x 48, 1024 = 16 x 64 / 8 x 128 / 32 x 32

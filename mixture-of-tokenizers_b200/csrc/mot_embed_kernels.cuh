@@ -180,37 +180,62 @@ __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s,
 // MODE 0 and MODE 4 decide every variant flag at run time; MODE 4 additionally handles the dense addend (kept out of
 // MODE 0 so that the common kernels do not carry its registers)
 #define MOT_RT(M) ((M) == 0 || (M) == 4)
+// MODE 5: plain token gather (no norm, no lambdas): the value embeddings (runs/7:308);
+// MODE 16 + f: the ADD family with its flags fixed at compile time, f = tok_norm | byte_norm << 1 | out_norm << 2 |
+//   lambdas << 3 (runs/73: f = 3, runs/74: 11, runs/71041..66: 15), byte table in shared memory.  The run-time-flag
+//   kernel spends most of its instructions re-deciding these per chunk (2350 warp instructions per occurrence at
+//   1024 columns, profiles/r1_bwd_generic_ncu.txt).
+#define MOT_ADDFAM(M) ((M) >= 16)
+#define MOT_ADDFLAG(M, bit) (MOT_ADDFAM(M) && (((M) - 16) & (bit)) != 0)
 template <int MODE>
 struct Cfg {
-  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) { return MODE == 2 || (MOT_RT(MODE) && (p.flags & MOT_F_TOK_NORM)); }
-  __device__ __forceinline__ static bool byte_scale(const EmbedParams& p) {
-    return MODE == 3 || (MOT_RT(MODE) && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN));
+  __device__ __forceinline__ static bool tok_norm(const EmbedParams& p) {
+    return MODE == 2 || MOT_ADDFLAG(MODE, 1) || (MOT_RT(MODE) && (p.flags & MOT_F_TOK_NORM));
   }
-  __device__ __forceinline__ static bool has_lam(const EmbedParams& p) { return MOT_RT(MODE) && (p.flags & MOT_F_HAS_LAMBDAS); }
-  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) { return MODE == 1 || (MOT_RT(MODE) && (p.flags & MOT_F_OUT_NORM)); }
-  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) { return MODE == 1 || MODE == 2 || (MOT_RT(MODE) && p.combine != MOT_BYTES_ONLY); }
-  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) { return MODE == 1 || MODE == 3 || (MOT_RT(MODE) && p.combine != MOT_TOK_ONLY); }
+  __device__ __forceinline__ static bool byte_scale(const EmbedParams& p) {
+    return MODE == 3 || MOT_ADDFLAG(MODE, 2 | 8) ||
+           (MOT_RT(MODE) && ((p.flags & (MOT_F_BYTE_NORM | MOT_F_HAS_LAMBDAS)) || p.combine == MOT_MEAN));
+  }
+  __device__ __forceinline__ static bool has_lam(const EmbedParams& p) {
+    return MOT_ADDFLAG(MODE, 8) || (MOT_RT(MODE) && (p.flags & MOT_F_HAS_LAMBDAS));
+  }
+  __device__ __forceinline__ static bool out_norm(const EmbedParams& p) {
+    return MODE == 1 || MOT_ADDFLAG(MODE, 4) || (MOT_RT(MODE) && (p.flags & MOT_F_OUT_NORM));
+  }
+  __device__ __forceinline__ static bool has_tok(const EmbedParams& p) {
+    return MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_BYTES_ONLY);
+  }
+  __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) {
+    return MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_TOK_ONLY);
+  }
   __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MOT_RT(MODE) && p.combine == MOT_MEAN; }
+  // the token part / the byte part carries a scale that is not identically 1 (a norm or a lambda)
+  static constexpr bool kTokScaled = MOT_RT(MODE) || MODE == 2 || MOT_ADDFLAG(MODE, 1 | 8);
+  static constexpr bool kLam = MOT_RT(MODE) || MOT_ADDFLAG(MODE, 8);
 };
 inline int pick_mode(const EmbedParams& p, int cw) {
   if (p.addend != nullptr || p.d_addend != nullptr) return 4;  // the dense addend has its own instantiations
   const int f = p.flags & (MOT_F_TOK_NORM | MOT_F_BYTE_NORM | MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS);
   if (p.Do % (32 * cw) != 0) return 0;
   if (p.combine == MOT_ADD && f == MOT_F_OUT_NORM && p.tab_smem) return 1;
+  if (p.combine == MOT_ADD && p.tab_smem)
+    return 16 + ((f & MOT_F_TOK_NORM) ? 1 : 0) + ((f & MOT_F_BYTE_NORM) ? 2 : 0) + ((f & MOT_F_OUT_NORM) ? 4 : 0) +
+           ((f & MOT_F_HAS_LAMBDAS) ? 8 : 0);
+  if (p.combine == MOT_TOK_ONLY && f == 0) return 5;
   if (p.combine == MOT_TOK_ONLY && f == MOT_F_TOK_NORM) return 2;
   if (p.combine == MOT_BYTES_ONLY && f == MOT_F_BYTE_NORM && p.tab_smem) return 3;
   return 0;
 }
 
-#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || (MOT_RT(MODE) && cm[it].toff >= 0))
-#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || (MOT_RT(MODE) && cm[it].slot >= 0))
+#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && cm[it].toff >= 0))
+#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && cm[it].slot >= 0))
 // element offset of chunk `it` in the token row: affine (base + immediate addressing) on the fast path
-#define MOT_TOFF(it) ((MODE == 1 || MODE == 2) ? ((it) * 32 + lane) * CW : cm[it].toff)
+#define MOT_TOFF(it) ((MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE)) ? ((it) * 32 + lane) * CW : cm[it].toff)
 #define MOT_CHUNK_OK(it) (!MOT_RT(MODE) || ((it) * 32 + lane) * CW < p.Do)
 
 template <typename T, int MODE = 0, int CW = 8>
 __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
-  if (MODE == 1 || MODE == 3) return Vec<T, CW>::lds_raw(tab + off);  // fast paths are only dispatched when the table fits
+  if (MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE)) return Vec<T, CW>::lds_raw(tab + off);  // only dispatched when the table fits
   return p.tab_smem ? Vec<T, CW>::lds_raw(tab + off) : Vec<T, CW>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
@@ -518,7 +543,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
         V::unpack(V::lds_raw(trow_smem + MOT_TOFF(it)), tv);
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e] - b * tv[e];
-      } else if (MOT_RT(MODE)) {
+      } else if (C::kLam) {
 #pragma unroll
         for (int e = 0; e < CW; ++e) o[e] = a * Du[it][e];
       } else {
@@ -764,7 +789,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 
       int idv[CPL];  // byte id of this lane's slot per chunk (warp collective: outside lane-dependent branches)
 #pragma unroll
-      for (int it = 0; it < CPL; ++it) idv[it] = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
+      for (int it = 0; it < CPL; ++it) idv[it] = has_bytes ? __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31) : 0;
       // z = tscale * t + lam_b * rs * b
       float z[CPL][CW], gr[CPL][CW];  // mixed row and upstream gradient row of this occurrence (only with out_norm)
       float ss = 0.f, gz = 0.f;
@@ -773,7 +798,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
       for (int it = 0; it < CPL; ++it) {
         if (has_tok && MOT_TOK_OK(it)) {
           V::unpack(V::lds_raw(trow + MOT_TOFF(it)), z[it]);
-          if (MOT_RT(MODE)) {
+          if (C::kTokScaled) {
 #pragma unroll
             for (int e = 0; e < CW; ++e) z[it][e] *= tscale;
           }
@@ -882,7 +907,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
               for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
             }
-            if (MOT_RT(MODE)) {
+            if (C::kLam) {
 #pragma unroll
               for (int e = 0; e < CW; ++e) dz[e] *= lam_b_eff;
             }
@@ -1117,7 +1142,7 @@ static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   EmbedParams p = p_in;
   const size_t smem = plan_smem(p, sizeof(T), kBwdThreads / 32, true, optin);
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
-  if ((MODE == 1 || MODE == 3) && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
+  if ((MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE)) && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
   auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
@@ -1133,6 +1158,8 @@ int dispatch_fwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
+int dispatch_bwd_static_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 5 / 16+f instantiations; -1: none
+int dispatch_bwd_gather_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_sum_bf16(const EmbedParams& p, cudaStream_t s);  // saved-output MoT-sum kernel; -1: not applicable
 int dispatch_bwd_sum_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_fwd_addend_bf16(const EmbedParams& p, cudaStream_t s);  // MODE 4 instantiations
