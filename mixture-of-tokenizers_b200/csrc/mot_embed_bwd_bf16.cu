@@ -10,7 +10,7 @@ int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s) {
     const int rc = dispatch_bwd_split_bf16(p, mode, s);
     if (rc >= 0) return rc;
   }
-  if (mode == 5 || mode >= 16) {  // plain gather / ADD family with compile-time flags
+  if (mode == 5 || mode == 6 || mode >= 16) {  // plain gather / ADD family with compile-time flags
     const int rc = dispatch_bwd_static_bf16(p, mode, s);
     if (rc >= 0) return rc;
   }

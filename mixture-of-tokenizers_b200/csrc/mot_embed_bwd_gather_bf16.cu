@@ -12,4 +12,10 @@ int dispatch_bwd_gather_bf16(const EmbedParams& p, cudaStream_t s) {
   }
   return -1;
 }
+// Pure concat under one output norm (MODE 6, runs/711:224-232: 512 + 16 x 32 = 1024 columns).
+int dispatch_bwd_concat_bf16(const EmbedParams& p, cudaStream_t s) {
+  using T = __nv_bfloat16;
+  if (p.Do / (32 * kBwdCW) == 8) return launch_bwd<T, 8, 6>(p, s);
+  return -1;
+}
 }  // namespace mot

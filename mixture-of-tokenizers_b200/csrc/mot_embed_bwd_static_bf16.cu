@@ -6,6 +6,7 @@ int dispatch_bwd_static_bf16(const EmbedParams& p, int mode, cudaStream_t s) {
   using T = __nv_bfloat16;
   const int cpl = p.Do / (32 * kBwdCW);  // exact: pick_mode checked Do % 128 == 0
   if (mode == 5) return dispatch_bwd_gather_bf16(p, s);
+  if (mode == 6) return dispatch_bwd_concat_bf16(p, s);
 #define MOT_STATIC_CASE(F)                                  \
   case 16 + F:                                              \
     if (cpl == 4) return launch_bwd<T, 4, 16 + F>(p, s);    \

@@ -181,6 +181,7 @@ __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s,
 // MODE 0 so that the common kernels do not carry its registers)
 #define MOT_RT(M) ((M) == 0 || (M) == 4)
 // MODE 5: plain token gather (no norm, no lambdas): the value embeddings (runs/7:308);
+// MODE 6: pure concat with the output norm only (runs/711:224-232), token / byte columns decided per chunk;
 // MODE 16 + f: the ADD family with its flags fixed at compile time, f = tok_norm | byte_norm << 1 | out_norm << 2 |
 //   lambdas << 3 (runs/73: f = 3, runs/74: 11, runs/71041..66: 15), byte table in shared memory.  The run-time-flag
 //   kernel spends most of its instructions re-deciding these per chunk (2350 warp instructions per occurrence at
@@ -200,13 +201,13 @@ struct Cfg {
     return MOT_ADDFLAG(MODE, 8) || (MOT_RT(MODE) && (p.flags & MOT_F_HAS_LAMBDAS));
   }
   __device__ __forceinline__ static bool out_norm(const EmbedParams& p) {
-    return MODE == 1 || MOT_ADDFLAG(MODE, 4) || (MOT_RT(MODE) && (p.flags & MOT_F_OUT_NORM));
+    return MODE == 1 || MODE == 6 || MOT_ADDFLAG(MODE, 4) || (MOT_RT(MODE) && (p.flags & MOT_F_OUT_NORM));
   }
   __device__ __forceinline__ static bool has_tok(const EmbedParams& p) {
-    return MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_BYTES_ONLY);
+    return MODE == 1 || MODE == 2 || MODE == 5 || MODE == 6 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_BYTES_ONLY);
   }
   __device__ __forceinline__ static bool has_bytes(const EmbedParams& p) {
-    return MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_TOK_ONLY);
+    return MODE == 1 || MODE == 3 || MODE == 6 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && p.combine != MOT_TOK_ONLY);
   }
   __device__ __forceinline__ static bool mean(const EmbedParams& p) { return MOT_RT(MODE) && p.combine == MOT_MEAN; }
   // the token part / the byte part carries a scale that is not identically 1 (a norm or a lambda)
@@ -222,20 +223,21 @@ inline int pick_mode(const EmbedParams& p, int cw) {
     return 16 + ((f & MOT_F_TOK_NORM) ? 1 : 0) + ((f & MOT_F_BYTE_NORM) ? 2 : 0) + ((f & MOT_F_OUT_NORM) ? 4 : 0) +
            ((f & MOT_F_HAS_LAMBDAS) ? 8 : 0);
   if (p.combine == MOT_TOK_ONLY && f == 0) return 5;
+  if (p.combine == MOT_CONCAT && f == MOT_F_OUT_NORM && p.tab_smem) return 6;
   if (p.combine == MOT_TOK_ONLY && f == MOT_F_TOK_NORM) return 2;
   if (p.combine == MOT_BYTES_ONLY && f == MOT_F_BYTE_NORM && p.tab_smem) return 3;
   return 0;
 }
 
-#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && cm[it].toff >= 0))
-#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE) || (MOT_RT(MODE) && cm[it].slot >= 0))
+#define MOT_TOK_OK(it) (MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE) || ((MOT_RT(MODE) || MODE == 6) && cm[it].toff >= 0))
+#define MOT_BYTE_OK(it) (MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE) || ((MOT_RT(MODE) || MODE == 6) && cm[it].slot >= 0))
 // element offset of chunk `it` in the token row: affine (base + immediate addressing) on the fast path
 #define MOT_TOFF(it) ((MODE == 1 || MODE == 2 || MODE == 5 || MOT_ADDFAM(MODE)) ? ((it) * 32 + lane) * CW : cm[it].toff)
 #define MOT_CHUNK_OK(it) (!MOT_RT(MODE) || ((it) * 32 + lane) * CW < p.Do)
 
 template <typename T, int MODE = 0, int CW = 8>
 __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& p, const T* tab, size_t off) {
-  if (MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE)) return Vec<T, CW>::lds_raw(tab + off);  // only dispatched when the table fits
+  if (MODE == 1 || MODE == 3 || MODE == 6 || MOT_ADDFAM(MODE)) return Vec<T, CW>::lds_raw(tab + off);  // only dispatched when the table fits
   return p.tab_smem ? Vec<T, CW>::lds_raw(tab + off) : Vec<T, CW>::ldg_raw(reinterpret_cast<const T*>(p.E_byte) + off);
 }
 
@@ -563,8 +565,16 @@ struct Batch {
   int chunk, sub;  // stream chunk and batch index inside the chunk
 };
 
+// CTA size of the backward: 12 warps; the widest ADD-family kernel with an output norm (32 columns per lane kept for the
+// mixed row and the accumulator) runs 8 warps so that it fits the register file without spilling.
+#ifndef MOT_WIDE_STATIC_THREADS
+#define MOT_WIDE_STATIC_THREADS 256
+#endif
+template <int CPL, int MODE>
+constexpr int bwd_threads() { return (MOT_ADDFLAG(MODE, 4) && CPL >= 8) ? MOT_WIDE_STATIC_THREADS : kBwdThreads; }
+
 template <typename T, int CPL, int MODE>
-__global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedParams p) {
+__global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(const EmbedParams p) {
   using C = Cfg<MODE>;
   constexpr int CW = kBwdCW;
   using V = Vec<T, CW>;
@@ -791,7 +801,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
 #pragma unroll
       for (int it = 0; it < CPL; ++it) idv[it] = has_bytes ? __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31) : 0;
       // z = tscale * t + lam_b * rs * b
-      float z[CPL][CW], gr[CPL][CW];  // mixed row and upstream gradient row of this occurrence (only with out_norm)
+      float z[CPL][CW];  // mixed row of this occurrence (only with out_norm)
       float ss = 0.f, gz = 0.f;
       if (out_norm) {
 #pragma unroll
@@ -841,15 +851,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
           for (int e = 0; e < CW; ++e) z[it][e] += ad[e];
         }
         if (MOT_CHUNK_OK(it)) {
-          V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), gr[it]);
+          float g4[CW];  // not kept across the reduction: the second pass reads the staged row again (registers)
+          V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), g4);
 #pragma unroll
           for (int e = 0; e < CW; ++e) {
             ss += z[it][e] * z[it][e];
-            gz += gr[it][e] * z[it][e];
+            gz += g4[e] * z[it][e];
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < CW; ++e) gr[it][e] = 0.f;
         }
       }
       }
@@ -865,8 +873,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mot_bwd_kernel(const EmbedPara
         float dz[CW];
         if (valid) {
           if (out_norm) {
+            float g4[CW];
+            V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), g4);
 #pragma unroll
-            for (int e = 0; e < CW; ++e) dz[e] = r_o * gr[it][e] - coef * z[it][e];
+            for (int e = 0; e < CW; ++e) dz[e] = r_o * g4[e] - coef * z[it][e];
           } else {  // no norm over the mixed row: dz is the upstream gradient itself
             V::unpack(V::lds_raw(grow + (size_t)(it * 32 + lane) * CW), dz);
           }
@@ -1140,13 +1150,14 @@ static int launch_bwd(const EmbedParams& p_in, cudaStream_t s) {
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   EmbedParams p = p_in;
-  const size_t smem = plan_smem(p, sizeof(T), kBwdThreads / 32, true, optin);
+  constexpr int NT = bwd_threads<CPL, MODE>();
+  const size_t smem = plan_smem(p, sizeof(T), NT / 32, true, optin);
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
-  if ((MODE == 1 || MODE == 3 || MOT_ADDFAM(MODE)) && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
+  if ((MODE == 1 || MODE == 3 || MODE == 6 || MOT_ADDFAM(MODE)) && !p.tab_smem) return launch_bwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
   auto kern = mot_bwd_kernel<T, CPL, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
-  launch_pdl(kern, dim3((unsigned)sms), dim3(kBwdThreads), smem, s, p);
+  launch_pdl(kern, dim3((unsigned)sms), dim3(NT), smem, s, p);
   if (g_prof_stop) cudaEventRecord(g_prof_stop, s);
   count_launch();
   return check_launch();
@@ -1160,6 +1171,7 @@ int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
 int dispatch_bwd_static_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 5 / 16+f instantiations; -1: none
 int dispatch_bwd_gather_bf16(const EmbedParams& p, cudaStream_t s);
+int dispatch_bwd_concat_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_sum_bf16(const EmbedParams& p, cudaStream_t s);  // saved-output MoT-sum kernel; -1: not applicable
 int dispatch_bwd_sum_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_fwd_addend_bf16(const EmbedParams& p, cudaStream_t s);  // MODE 4 instantiations
