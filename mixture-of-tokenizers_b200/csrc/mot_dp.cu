@@ -16,7 +16,7 @@ namespace mot {
 
 // Few, fat CTAs: the switch round trip is microseconds and the links saturate with about 1 MB in flight per rank; more
 // CTAs only add contention inside the switch (8 ranks, 77 MB bf16: 8 x 1024 threads 195 us, 16 x 1024 203 us, 36 x 1024
-// 219 us, 144 x 512 239 us, NCCL 270 us; gpurun_out/run6.log, exp_nvls8.log).
+// 219 us, 144 x 512 239 us, NCCL 270 us; profiles/r1_experiments.md).
 constexpr int kArThreads = 1024;
 constexpr int kArMaxBlocks = 8;     // signal-pad slots used: blocks x world uint32 (torch's pad is 9216 B = 2304 slots)
 

@@ -354,7 +354,7 @@ static bool saved_path_applies(const MotDesc* d, const EmbedParams& p) {
   if (!(cpl == 4 || cpl == 6 || cpl == 8 || (d->dtype == MOT_F32 && cpl == 2))) return false;
   // Beyond ~4 positions per vocabulary row the recompute kernel wins: its token rows are re-read from L2 (the
   // sorted stream visits a row's occurrences back to back) while the saved rows are all distinct HBM reads
-  // (768 = 16 x 48 bf16, V = 50257: 131K tokens 118 vs 132 us, 262K 225 vs 218 us, 1M 921 vs 795 us; gpurun_out/run4.log).
+  // (768 = 16 x 48 bf16, V = 50257: 131K tokens 118 vs 132 us, 262K 225 vs 218 us, 1M 921 vs 795 us; profiles/r1_experiments.md).
   return p.N <= 4LL * p.V;
 }
 

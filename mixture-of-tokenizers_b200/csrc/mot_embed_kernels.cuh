@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
 // Pick the ring depth and whether the byte table fits next to it; returns dynamic smem bytes or 0.
 inline size_t plan_smem(EmbedParams& p, size_t esz, int warps, bool backward, int optin) {
   static const char* env_st = getenv("MOT_STAGES");  // debug knob
-  const int want = env_st ? atoi(env_st) : 2;  // measured: 2 stages per warp are as fast as 4 (gpurun_out/exp3.log)
+  const int want = env_st ? atoi(env_st) : 2;  // measured: 2 stages per warp are as fast as 4 (profiles/r1_experiments.md)
   p.tab_smem = 1;
   for (int tab = 1; tab >= 0; --tab) {
     p.tab_smem = tab;

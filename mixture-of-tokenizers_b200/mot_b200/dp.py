@@ -31,7 +31,7 @@ def broadcast_params(params: Iterable[torch.Tensor], src: int = 0, group=None) -
 
 def own_allreduce_pays(group=None) -> bool:
     """Whether the library's NVLS all-reduce beats NCCL for the gradient bucket of this path (77 MB bf16 at the
-    124M shape).  Measured on 8xB200 / NVSwitch (gpurun_out/exp_nvls8.log, run5.log): 8 ranks 215 us vs NCCL 270 us;
+    124M shape).  Measured on 8xB200 / NVSwitch (profiles/r1_experiments.md): 8 ranks 215 us vs NCCL 270 us;
     4 ranks 235 vs 214 us; 2 ranks 226 vs 174 us.  Through the switch every rank moves S*(1 + 1/n) bytes per
     direction (its own slice also travels to the switch and back), NCCL's ring 2*S*(n-1)/n: the in-switch reduction
     wins from n = 8 on.  MOT_DP_OWN=1 / MOT_DP_NCCL=1 force either."""
