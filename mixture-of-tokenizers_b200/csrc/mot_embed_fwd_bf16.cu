@@ -4,7 +4,12 @@ namespace mot {
 int dispatch_fwd_bf16(const EmbedParams& p, cudaStream_t s) {
   using T = __nv_bfloat16;
   const int cpl = (p.n_chunks + 31) / 32;
-  if (pick_mode(p, 8) == 1) {  // MoT-sum fast path (runs/71), the shapes the reference ships
+  const int mode = pick_mode(p, 8);
+  if (mode >= 16) {  // ADD family with compile-time flags
+    const int rc = dispatch_fwd_static_bf16(p, mode, s);
+    if (rc >= 0) return rc;
+  }
+  if (mode == 1) {  // MoT-sum fast path (runs/71), the shapes the reference ships
     if (cpl == 3) return launch_fwd<T, 3, 1>(p, s);
     if (cpl == 4) return launch_fwd<T, 4, 1>(p, s);
   }

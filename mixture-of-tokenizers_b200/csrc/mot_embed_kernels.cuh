@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     float ss = 0.f;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
-      if (MOT_RT(MODE)) {
+      if (C::kTokScaled) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[it][e] *= tscale;
       }
@@ -1131,7 +1131,7 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
     if (smem != 0 && (p.tab_smem || p.combine == MOT_TOK_ONLY || threads == 256)) break;
   }
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
-  if (MODE == 1 && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast path assumes the table in smem
+  if ((MODE == 1 || MOT_ADDFAM(MODE)) && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
   auto kern = mot_fwd_kernel<T, CPL, MODE, NT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   const long long warps_needed = p.N;
@@ -1169,6 +1169,7 @@ int dispatch_fwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_f32(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_split_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 2 / 3 instantiations
+int dispatch_fwd_static_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 16+f forward instantiations; -1: none
 int dispatch_bwd_static_bf16(const EmbedParams& p, int mode, cudaStream_t s);  // MODE 5 / 16+f instantiations; -1: none
 int dispatch_bwd_gather_bf16(const EmbedParams& p, cudaStream_t s);
 int dispatch_bwd_concat_bf16(const EmbedParams& p, cudaStream_t s);

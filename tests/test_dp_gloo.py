@@ -36,7 +36,10 @@ def _worker(rank, world, port, q):
         mine = dp.shard_for_rank(stream, pos=100, local=64, rank=rank)
         assert mine[0].item() == 100 + rank * 64 and mine.numel() == 64
         # one flat bucket, per-parameter views, one collective
-        bucket = dp.GradBucket([E_tok, E_byte])
+        # "auto": the own NVLS all-reduce only from 8 ranks up (measured), never without CUDA + multicast
+        assert dp.own_allreduce_pays() is False
+        bucket = dp.GradBucket([E_tok, E_byte], symmetric="auto")
+        assert bucket._symm is None
         v_tok, v_byte = bucket.views()
         assert v_tok.shape == E_tok.shape and v_byte.shape == E_byte.shape
         assert v_tok.data_ptr() == bucket.flat.data_ptr() and bucket.offsets[1] % 4 == 0
