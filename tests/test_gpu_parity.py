@@ -286,11 +286,16 @@ def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V,
     res = {}
     for name, kw in (("saved", dict(out_saved=out, rstd=rstd)), ("recompute", {})):
         for rep in range(2):   # twice on the same workspace: the first call leaves it clean for the second
-            gt = torch.full_like(Et, float("nan"))
-            gb = torch.full_like(Eb, float("nan"))
+            # dense gradients inside guard rows: a write outside [0, V) x [0, Dt) would clear a NaN sentinel
+            gt_buf = torch.full((V + 2, Dt), float("nan"), dtype=dtype, device=d)
+            gb_buf = torch.full((458 + 2, bd), float("nan"), dtype=dtype, device=d)
+            gt, gb = gt_buf[1:-1], gb_buf[1:-1]
             ops.embed_backward_out(desc, tk, idd, None, Et, Eb, None, go, gt, gb, None, ws, plan_ready=False,
                                    ws_clean=(rep == 1 or name == "recompute"), **kw)
             torch.cuda.synchronize()
+            for buf in (gt_buf, gb_buf):
+                assert bool(torch.isnan(buf[0]).all()) and bool(torch.isnan(buf[-1]).all()), f"{name}: write outside the table"
+                assert not bool(torch.isnan(buf[1:-1]).any()), f"{name}: a row was not written"
         res[name] = (gt, gb)
     tol = TOL[dtype]
     assert nerr(out, want_out) <= tol
