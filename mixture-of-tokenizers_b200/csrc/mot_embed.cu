@@ -415,7 +415,6 @@ extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void
   p.gout = grad_out; p.gE_tok = gE_tok; p.gE_byte = gE_byte; p.g_lam = g_lam;
   p.addend = addend; p.d_addend = d_addend;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const size_t esz = d->dtype == MOT_BF16 ? 2 : 4;
   if (!plan_ready) {
     if (!ws_clean && cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
     if (int rc = run_plan(p, s)) return rc;

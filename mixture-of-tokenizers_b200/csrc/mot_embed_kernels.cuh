@@ -613,7 +613,6 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
   //      CTAs, so every SM gets the same number of chunks +-1), walked in batches of 32 entries (one per lane) ----
   const int Ni = (int)p.N;  // n_tokens < 2^31 (validated on the host): 32-bit stream math
   const int n_stream_chunks = (Ni + p.R - 1) / p.R;
-  const int bpc = (p.R + 31) / 32;  // batches per chunk
   int nx_chunk = gw, nx_sub = 0;    // the next batch to load
   auto load_next = [&](Batch& b) {
     b.pos = 0;

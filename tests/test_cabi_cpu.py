@@ -140,3 +140,37 @@ def test_saved_backward_query_needs_no_device():
     assert lib.mot_embed_bwd_uses_saved(desc(flags=L.F_OUT_NORM | L.F_TOK_NORM)) == 0
     assert lib.mot_embed_bwd_uses_saved(desc(combine=L.CONCAT, out_dim=768 + 16 * 48)) == 0
     assert lib.mot_embed_bwd_uses_saved(desc(abi_version=9)) == 0
+
+
+def test_new_entry_points_validate_before_touching_the_device():
+    lib = L.lib()
+    null = None
+    # byte-pair kernels (spt/train_gpt.py:371-379): sizes, alignment and dtype are checked first
+    args = dict(ids_i64=1, n=4, bpt=16, Vb=458, bd=48, dtype=L.BF16, eps=1e-7, ld=256 + 16 * 48, col=256)
+
+    def pair_fwd(**kw):
+        a = {**args, **kw}
+        return lib.mot_byte_pair_fwd(null, null, a["ids_i64"], a["n"], a["bpt"], null, a["Vb"], a["bd"], a["dtype"], a["eps"], null,
+                                     a["ld"], a["col"], null)
+    assert pair_fwd() == L.ERR_BAD_ARG                       # null pointers
+    assert pair_fwd(n=0) == L.OK                             # empty batch: nothing to do
+    assert pair_fwd(bd=44) == L.ERR_MISALIGNED
+    assert pair_fwd(col=4) == L.ERR_MISALIGNED
+    assert pair_fwd(ld=256) == L.ERR_BAD_ARG                 # rows narrower than col + bpt*bd
+    assert pair_fwd(bpt=33) == L.ERR_BAD_ARG
+    assert pair_fwd(dtype=7) == L.ERR_UNSUPPORTED
+    assert lib.mot_byte_pair_workspace_bytes(458, 48) == 16 * 458 * 48 * 4 and lib.mot_byte_pair_workspace_bytes(0, 48) == 0
+    assert lib.mot_byte_pair_bwd(null, null, 1, 4, 16, null, 458, 48, L.BF16, 1e-7, null, 1024, 256, null, null, 0, null) == L.ERR_BAD_ARG
+    # uint16 -> int32 widening of shard tokens
+    assert lib.mot_tokens_widen_u16(null, 0, null, null) == L.OK
+    assert lib.mot_tokens_widen_u16(null, 8, null, null) == L.ERR_BAD_ARG
+    assert lib.mot_tokens_widen_u16(null, -1, null, null) == L.ERR_BAD_ARG
+    # extended forward / backward: the dense addend is refused with a split concat or strided rows, never dropped
+    one = C.c_void_p(16)
+    split = desc(combine=L.CONCAT, out_dim=768 + 16 * 48, flags=L.F_TOK_NORM | L.F_BYTE_NORM)
+    assert lib.mot_embed_fwd_ex(split, null, null, null, null, null, null, one, null, null, null) == L.ERR_UNSUPPORTED
+    strided = desc(combine=L.TOK_ONLY, out_dim=768, byte_dim=8, row_stride=2048, col_offset=0)
+    assert lib.mot_embed_fwd_ex(strided, null, null, null, null, null, null, one, null, null, null) == L.ERR_UNSUPPORTED
+    assert lib.mot_embed_workspace_bytes(desc(row_stride=512)) == 0          # rows narrower than out_dim
+    assert lib.mot_embed_workspace_bytes(desc(row_stride=1024, col_offset=4)) == 0
+    assert lib.mot_embed_workspace_bytes(desc(row_stride=1024, col_offset=256)) > 0
