@@ -938,7 +938,13 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
     A = B;
     if (iw == 1) iw = 0; else ik = 0;
     load_next(B);
-    while (issued - consumed < D && try_issue()) {  // the issue cursor may have been waiting for this batch
+    // the issue cursor may have been waiting for this batch.  An open row whose flush reads its token row (token norm /
+    // lambdas) still needs the most recently consumed stage `ps`: the refill must leave that one stage alone until the
+    // flush at the next row change (the issue order fills the OLDEST free stage first, so keeping one stage free is
+    // keeping `ps`).  Without this a row ending exactly at a 32-entry batch boundary inside a chunk (chunks longer than
+    // one batch: more than 56832 tokens) was normalised against a half-overwritten token row.
+    const int hold = (cur_v >= 0 && need_trow && (tok_norm || has_lam)) ? 1 : 0;
+    while (issued - consumed < D - hold && try_issue()) {
     }
   }
 

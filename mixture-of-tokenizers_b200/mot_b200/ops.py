@@ -367,6 +367,10 @@ class _MotEmbedFn(torch.autograd.Function):
         keep = needs_grad and n > 0 and bool(L.lib().mot_embed_bwd_uses_saved(desc))
         rstd = torch.empty(n, dtype=torch.float32, device=dev) if keep else None
         embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st, rstd=rstd)
+        if ctx.ws is not None and torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture (torch.cuda.graph / make_graphed_callables): the side stream must rejoin before the
+            # capture of the forward ends; the graph keeps plan and forward concurrent
+            embed_plan_join(ctx.ws, dev, st)
         ctx.desc, ctx.dev = desc, dev
         saved = (tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out if keep else None, rstd)
         ctx.save_for_backward(*[t if t is not None else _ABSENT for t in saved])
@@ -398,7 +402,8 @@ class _MotEmbedFn(torch.autograd.Function):
         if ws is None:
             ws = acquire_workspace(desc, dev)
         if planned:
-            embed_plan_join(ws, dev, st)
+            if ws.pending:        # not yet joined (a captured forward joins at its own end)
+                embed_plan_join(ws, dev, st)
             clean = True          # the plan ran on a clean (or freshly cleared) workspace and leaves it clean
         else:
             clean, ws.clean = ws.clean, False

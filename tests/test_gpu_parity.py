@@ -308,6 +308,50 @@ def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V,
         assert float(res["saved"][0][untouched.to(d)].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("variant", ["V3d", "V3b", "V4"])
+def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
+    """The compile-time-flag backward kernels at the shipped sizes (65536 tokens, V = 50257, 1024 columns, bf16), where
+    the CPU oracle is too slow: the same formulas restated with torch fp32 ops on the GPU (test-only) through autograd."""
+    import mot_b200
+    import torch.nn.functional as F
+    d = dev()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    N, V, bpt = 65536, 50257, 16
+    Dt, bd = (512, 32) if variant == "V4" else (1024, 64)
+    toks = torch.randint(0, V, (N,), generator=g, device=d, dtype=torch.int32)
+    slot_major = variant != "V4"
+    ids = torch.randint(0, 458, (bpt, N) if slot_major else (1, N * bpt), generator=g, device=d, dtype=torch.int32)
+    Et = torch.randn(V, Dt, generator=g, device=d).bfloat16().requires_grad_(True)
+    Eb = torch.randn(458, bd, generator=g, device=d).bfloat16().requires_grad_(True)
+    lam = torch.tensor([0.7, 0.4], device=d, requires_grad=True) if variant == "V3d" else None
+    Do = Dt + bpt * bd if variant == "V4" else Dt
+    gout = torch.randn(N, Do, generator=g, device=d).bfloat16()
+    spec = mot_b200.MixSpec(**mot_b200.RUN_VARIANTS[variant])
+    out = mot_b200.mot_embed(toks, ids, Et, Eb, spec, bpt=bpt, lam=lam)
+    out.backward(gout)
+    # restatement (runs/71041:311-313, runs/73:313-315, runs/711:314-316)
+    Etf, Ebf = Et.detach().float().requires_grad_(True), Eb.detach().float().requires_grad_(True)
+    lamf = lam.detach().clone().requires_grad_(True) if lam is not None else None
+    nrm = lambda x: F.rms_norm(x, (x.size(-1),), eps=mot_b200.FP32_EPS)  # noqa: E731
+    t = Etf[toks.long()]
+    idm = ids.long().t() if slot_major else ids.long().view(N, bpt)
+    b = Ebf[idm]                                   # [N, bpt, bd]
+    if variant == "V4":
+        ref = nrm(torch.cat([t, b.reshape(N, -1)], dim=-1))
+    else:
+        tn, bn = nrm(t), nrm(b).reshape(N, -1)
+        if variant == "V3d":
+            ref = nrm(tn * lamf[0] + bn * lamf[1])
+        else:
+            ref = tn + bn
+    ref.backward(gout.float())
+    assert nerr(out, ref) <= 2.0 ** -8
+    assert nerr(Et.grad, Etf.grad) <= 2.0 ** -8, f"gE_tok {nerr(Et.grad, Etf.grad):.3e}"
+    assert nerr(Eb.grad, Ebf.grad) <= 2.0 ** -8, f"gE_byte {nerr(Eb.grad, Ebf.grad):.3e}"
+    if lam is not None:
+        assert float((lam.grad - lamf.grad).abs().max() / lamf.grad.abs().max()) <= 2.0 ** -8
+
+
 def test_unsupported_and_bad_arguments():
     import mot_b200
     d = dev()
