@@ -441,7 +441,8 @@ def run_ours(args):
                 def rel(a, b):
                     return float((a.float() - b.float()).abs().max()) / max(float(b.float().abs().max()), 1e-30)
                 errs = (rel(mod.embed_tokens.weight.grad, eager_ref_t), rel(mod.embed_bytes.weight.grad, eager_ref))
-                if not all(e <= 2.0 ** -8 for e in errs):     # also false for NaN
+                # two bf16 results of fp32 sums taken in different orders may differ by one bf16 ulp (2^-7 of an element)
+                if not all(e <= 2.0 ** -6 for e in errs):     # also false for NaN
                     raise RuntimeError(f"graphed step does not reproduce the eager gradients (normalised max-abs {errs})")
                 for _ in range(3):
                     e2e_step()
