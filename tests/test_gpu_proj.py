@@ -31,7 +31,8 @@ def nerr(a, b):
 
 
 @pytest.mark.parametrize("n,K,Do", [(1, 64, 8), (37, 160, 40), (128, 64, 256), (300, 1024, 1024), (777, 1920, 1000),
-                                    (4096, 2048, 1024)])
+                                    (4096, 2048, 1024),
+                                    (40000, 512, 1024)])   # 1252 output tiles: several tiles per persistent CTA
 def test_linear_kernels_match_fp32_matmul(n, K, Do):
     from mot_b200 import ops
     d = dev()

@@ -62,6 +62,23 @@ def test_value_embeddings_match_oracle(dtype, V, D, N, zipf):
             assert float(got[untouched.to(d)].abs().max()) == 0.0
 
 
+def test_value_embeddings_full_size_vs_index_add():
+    """65536 tokens over the GPT-2 vocabulary, 1024 columns (stream chunks of two batches): the dense gradient against
+    torch's index_add_ in fp32 on the GPU (test-only)."""
+    import mot_b200
+    d = dev()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    N, V, D = 65536, 50257, 1024
+    toks = torch.randint(0, V, (N,), generator=g, device=d, dtype=torch.int32)
+    E = torch.randn(V, D, generator=g, device=d).bfloat16().requires_grad_(True)
+    gout = torch.randn(N, D, generator=g, device=d).bfloat16()
+    (out,) = mot_b200.tok_gather(toks, E)
+    out.backward(gout)
+    assert torch.equal(out, E.detach()[toks.long()])
+    want = torch.zeros(V, D, device=d).index_add_(0, toks.long(), gout.float())
+    assert nerr(E.grad, want) <= 2.0 ** -8
+
+
 def test_value_embeddings_2d_tokens_and_shape_errors():
     import mot_b200
     d = dev()
