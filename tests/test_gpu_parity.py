@@ -308,7 +308,7 @@ def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V,
         assert float(res["saved"][0][untouched.to(d)].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", ["V3d", "V3b", "V4", "V1A"])
+@pytest.mark.parametrize("variant", ["V3d", "V3b", "V3c", "V4", "V1A", "V3_256k"])
 def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
     """The compile-time-flag backward kernels at the shipped sizes (65536 tokens, V = 50257, 1024 columns, bf16), where
     the CPU oracle is too slow: the same formulas restated with torch fp32 ops on the GPU (test-only) through autograd."""
@@ -318,18 +318,20 @@ def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
     g = torch.Generator(device="cuda").manual_seed(9)
     N, V, bpt = 65536, 50257, 16
     Dt, bd = (512, 32) if variant in ("V4", "V1A") else (1024, 64)
+    if variant == "V3_256k":      # more than 4 positions per vocabulary row: the recompute kernel, stream chunks of 5 batches
+        N, Dt, bd = 262144, 768, 48
     toks = torch.randint(0, V, (N,), generator=g, device=d, dtype=torch.int32)
     slot_major = variant not in ("V4", "V1A")
     ids = torch.randint(0, 458, (bpt, N) if slot_major else (1, N * bpt), generator=g, device=d, dtype=torch.int32)
     Et = torch.randn(V, Dt, generator=g, device=d).bfloat16().requires_grad_(True)
     Eb = torch.randn(458, bd, generator=g, device=d).bfloat16().requires_grad_(True)
-    lam = torch.tensor([0.7, 0.4], device=d, requires_grad=True) if variant == "V3d" else None
+    lam = torch.tensor([0.7, 0.4], device=d, requires_grad=True) if variant in ("V3d", "V3c") else None
     Do = Dt + bpt * bd if variant in ("V4", "V1A") else Dt
     gout = torch.randn(N, Do, generator=g, device=d).bfloat16()
     # V1A: the [norm(tok) | norm(bytes)] operand of the projection variants (runs/7:317-318), split into a tok-only and a
     # bytes-only launch
     spec = mot_b200.MixSpec(combine="concat", tok_norm=True, byte_norm=True, out_norm=False) if variant == "V1A" \
-        else mot_b200.MixSpec(**mot_b200.RUN_VARIANTS[variant])
+        else mot_b200.MixSpec(**mot_b200.RUN_VARIANTS["V3" if variant == "V3_256k" else variant])
     out = mot_b200.mot_embed(toks, ids, Et, Eb, spec, bpt=bpt, lam=lam)
     out.backward(gout)
     # restatement (runs/71041:311-313, runs/73:313-315, runs/711:314-316)
@@ -347,6 +349,10 @@ def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
         tn, bn = nrm(t), nrm(b).reshape(N, -1)
         if variant == "V3d":
             ref = nrm(tn * lamf[0] + bn * lamf[1])
+        elif variant == "V3c":
+            ref = tn * lamf[0] + bn * lamf[1]
+        elif variant == "V3_256k":
+            ref = nrm(t + b.reshape(N, -1))
         else:
             ref = tn + bn
     ref.backward(gout.float())
