@@ -308,7 +308,7 @@ def test_saved_output_backward_vs_recompute_and_oracle(dtype, Dt, bd, bpt, N, V,
         assert float(res["saved"][0][untouched.to(d)].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("variant", ["V3d", "V3b", "V3c", "V4", "V1A", "V3_256k"])
+@pytest.mark.parametrize("variant", ["V3d", "V3b", "V3c", "V4", "V1A", "V3_256k", "V3_zipf", "V3d_zipf"])
 def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
     """The compile-time-flag backward kernels at the shipped sizes (65536 tokens, V = 50257, 1024 columns, bf16), where
     the CPU oracle is too slow: the same formulas restated with torch fp32 ops on the GPU (test-only) through autograd."""
@@ -321,6 +321,9 @@ def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
     if variant == "V3_256k":      # more than 4 positions per vocabulary row: the recompute kernel, stream chunks of 5 batches
         N, Dt, bd = 262144, 768, 48
     toks = torch.randint(0, V, (N,), generator=g, device=d, dtype=torch.int32)
+    if variant.endswith("_zipf"):   # hot rows spread over hundreds of stream chunks: fp32 slot + finalize path at scale
+        toks = (torch.rand(N, generator=g, device=d) ** 6 * V).long().clamp_(0, V - 1).int()
+        variant = variant[:-5]
     slot_major = variant not in ("V4", "V1A")
     ids = torch.randint(0, 458, (bpt, N) if slot_major else (1, N * bpt), generator=g, device=d, dtype=torch.int32)
     Et = torch.randn(V, Dt, generator=g, device=d).bfloat16().requires_grad_(True)
@@ -351,7 +354,7 @@ def test_full_size_static_flag_kernels_vs_torch_restatement(variant):
             ref = nrm(tn * lamf[0] + bn * lamf[1])
         elif variant == "V3c":
             ref = tn * lamf[0] + bn * lamf[1]
-        elif variant == "V3_256k":
+        elif variant in ("V3_256k", "V3"):
             ref = nrm(t + b.reshape(N, -1))
         else:
             ref = tn + bn
