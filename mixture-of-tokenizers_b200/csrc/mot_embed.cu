@@ -135,7 +135,7 @@ static int validate(const MotDesc* d) {
   if (d->out_dim > 8 * 32 * 8) return MOT_ERR_UNSUPPORTED;  // CPL <= 8
   if (d->row_stride != 0 || d->col_offset != 0) {  // a column slice of wider rows
     const long long ld = d->row_stride ? d->row_stride : d->out_dim;
-    if (d->col_offset < 0 || ld < (long long)d->col_offset + d->out_dim) return MOT_ERR_BAD_ARG;
+    if (d->col_offset < 0 || ld < (long long)d->col_offset + d->out_dim || ld > 0x7fffffffLL) return MOT_ERR_BAD_ARG;
     if (ld % 8 || d->col_offset % 8) return MOT_ERR_MISALIGNED;
   }
   if ((d->flags & MOT_F_IDS_FROM_TTB) && has_bytes) {

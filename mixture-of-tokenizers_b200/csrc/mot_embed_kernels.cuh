@@ -121,6 +121,8 @@ __device__ __forceinline__ ChunkMap chunk_map(const EmbedParams& p, int c) {
 }
 
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
+// row * width as ONE 32 x 32 -> 64 bit multiply (both factors are non-negative and < 2^31: validated on the host)
+__device__ __forceinline__ size_t mul_u32(int a, int b) { return (size_t)(unsigned)a * (unsigned)b; }
 
 // RAW byte id of (position, slot); slot < bpt.  The caller clamps it with clamp_id() where it is consumed,
 // one iteration later, so the load's latency is not exposed at the load site (the pipeline issues in order).
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     for (int i = 0; i < D && i < n_i; ++i) {
       const int tv = clampi(__ldg(p.tok + gw + i * stride), p.V - 1);
       mbar_expect_tx(bars + i, row_bytes);
-      bulk_g2s(ring + (size_t)i * L.stage_bytes, E_tok + (size_t)tv * p.Dt, row_bytes, bars + i);
+      bulk_g2s(ring + (size_t)i * L.stage_bytes, E_tok + mul_u32(tv, p.Dt), row_bytes, bars + i);
     }
     if (D < n_i) tok_ahead = __ldg(p.tok + gw + D * stride);  // raw; clamped where it is used
   }
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
             const int id = __shfl_sync(0xffffffffu, idreg, k);
             if (cm[it].slot == -2) {
               float b[8];
-              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
               const float bs = lam_b * rs[id];
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[it][e] += bs * b[e];
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
           const int id = __shfl_sync(0xffffffffu, idreg, cm[it].slot & 31);
           if (MOT_BYTE_OK(it)) {
             float b[8];
-            Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+            Vec8<T>::unpack(tab_load<T, MODE>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
             if (byte_scale) {
               const float bs = lam_b * rs[id];
 #pragma unroll
@@ -476,14 +478,14 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     }
     if (has_tok && lane == 0 && i + D < n_i) {
       mbar_expect_tx(bars + s, row_bytes);
-      bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + (size_t)clampi(tok_ahead, p.V - 1) * p.Dt, row_bytes, bars + s);
+      bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + mul_u32(clampi(tok_ahead, p.V - 1), p.Dt), row_bytes, bars + s);
       if (i + D + 1 < n_i) tok_ahead = __ldg(p.tok + pos + (D + 1) * stride);
     }
     if (++s == D) {
       s = 0;
       parity ^= 1u;
     }
-    T* orow = out + (size_t)pos * p.io_ld + p.io_col;
+    T* orow = out + mul_u32(pos, (int)p.io_ld) + p.io_col;
 #pragma unroll
     for (int it = 0; it < CPL; ++it) {
       if (MOT_CHUNK_OK(it)) {
@@ -535,7 +537,7 @@ __device__ __forceinline__ float finish_tok_row(const EmbedParams& p, const Chun
   // d that = lam_t * Du ; dt = r_t * d that - tv * r_t^3 * mean(d that . tv)
   const float a = lam_t * r_t;
   const float b = tok_norm ? lam_t * r_t * r_t * r_t * dot / (float)p.Dt : 0.f;
-  T* grow = reinterpret_cast<T*>(p.gE_tok) + (size_t)v * p.Dt;
+  T* grow = reinterpret_cast<T*>(p.gE_tok) + mul_u32(v, p.Dt);
 #pragma unroll
   for (int it = 0; it < CPL; ++it) {
     if (MOT_TOK_OK(it)) {
@@ -666,8 +668,8 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
       const int pos = iw ? B.pos : A.pos, v = iw ? B.v : A.v;
       unsigned char* st = ring + (size_t)is * L.stage_bytes;
       mbar_expect_tx(bars + is, g_bytes + t_bytes);
-      bulk_g2s(st, gout + (size_t)pos * p.io_ld + p.io_col, g_bytes, bars + is);
-      if (need_trow) bulk_g2s(st + L.g_bytes, E_tok + (size_t)v * p.Dt, t_bytes, bars + is);
+      bulk_g2s(st, gout + mul_u32(pos, (int)p.io_ld) + p.io_col, g_bytes, bars + is);
+      if (need_trow) bulk_g2s(st + L.g_bytes, E_tok + mul_u32(v, p.Dt), t_bytes, bars + is);
     }
     ++issued;
     if (++is == D) is = 0;
@@ -709,7 +711,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        T* row = G + (size_t)(vb + j) * p.Dt;
+        T* row = G + mul_u32(vb + j, p.Dt);
         for (int c = lane; c < p.Dt / CW; c += 32) V::stg(row + c * CW, zero);
       }
     }
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
       // the first chunk of at most one such row: its last one).  Hot rows spread over many chunks meet there through
       // the L2 atomic units; the finalize kernel reads the one slot, writes the row and zeroes the slot again.
       const int c_first = __ldg(p.off + cur_v) / p.R;
-      float* prow = p.partial + (size_t)c_first * p.Dt;
+      float* prow = p.partial + mul_u32(c_first, p.Dt);
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
         if (MOT_TOK_OK(it))
@@ -821,7 +823,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
               const int id = __shfl_sync(0xffffffffu, idreg, kk);
               if (cm[it].slot == -2) {
                 float b[CW];
-                V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                V::unpack(tab_load<T, MODE, CW>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
                 for (int e = 0; e < CW; ++e) z[it][e] += bs * b[e];
@@ -831,7 +833,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
             const int id = idv[it];
             if (MOT_BYTE_OK(it)) {
               float b[CW];
-              V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              V::unpack(tab_load<T, MODE, CW>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
               if (byte_scale) {
                 const float bs = lam_b_eff * rs[id];
 #pragma unroll
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
               if (valid && cm[it].slot == -2) {
                 if (has_lam) {
                   float b[CW];
-                  V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+                  V::unpack(tab_load<T, MODE, CW>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
                   const float r = rs[id] * inv_pool;
 #pragma unroll
                   for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
@@ -904,14 +906,14 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
                 float dzs[CW];
 #pragma unroll
                 for (int e = 0; e < CW; ++e) dzs[e] = dz[e] * lam_b_eff;
-                gmem_add4(accp + (size_t)id * p.bd + cm[it].boff, dzs);
+                gmem_add4(accp + (unsigned)(id * p.bd + cm[it].boff), dzs);
               }
             }
           } else if (valid && MOT_BYTE_OK(it)) {
             const int id = idv[it];
             if (has_lam) {  // d lam_byte += <dz, bhat>
               float b[CW];
-              V::unpack(tab_load<T, MODE, CW>(p, tab, (size_t)id * p.bd + cm[it].boff), b);
+              V::unpack(tab_load<T, MODE, CW>(p, tab, (unsigned)(id * p.bd + cm[it].boff)), b);
               const float r = rs[id];
 #pragma unroll
               for (int e = 0; e < CW; ++e) dlam_b += dz[e] * r * b[e];
@@ -920,7 +922,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
 #pragma unroll
               for (int e = 0; e < CW; ++e) dz[e] *= lam_b_eff;
             }
-            gmem_add4(accp + (size_t)id * p.bd + cm[it].boff, dz);
+            gmem_add4(accp + (unsigned)(id * p.bd + cm[it].boff), dz);
           }
         }
       }
