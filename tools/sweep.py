@@ -33,11 +33,14 @@ def embed_step(N, Dt, bd, dist):
     spec = mot_b200.MixSpec(combine="add", slot_major=True)
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=False, seq_len=N)
     ws = ops.acquire_workspace(desc, d)
+    # keep out + rstd where the library's saved-output backward would use them (up to 4 positions per vocabulary row)
+    rstd = torch.empty(N, dtype=torch.float32, device=d) if ops.embed_bwd_uses_saved(desc) else None
     def step():
         ops.embed_plan_async(desc, tok, ws, d)
-        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, out)
+        ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, out, rstd=rstd)
         ops.embed_plan_join(ws, d)
-        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, gout, gE_tok, gE_byte, None, ws.buf, plan_ready=True, ws_clean=True)
+        ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, gout, gE_tok, gE_byte, None, ws.buf, plan_ready=True,
+                               ws_clean=True, out_saved=out if rstd is not None else None, rstd=rstd)
         ws.clean = True
     return step
 
