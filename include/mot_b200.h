@@ -112,6 +112,20 @@ void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* 
 int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, int32_t tok_vocab, int32_t bpt,
                    int32_t ttb_dtype, void* out, int32_t out_i64, void* stream);
 
+/* ttb table build as an integer gather.  Replaces the loop body of create_ttb (modded-nanogpt/create_ttb.py:18-31):
+ * row v = the FIRST min(bpt, len_v) character ids of token v (`chars[offs[v] .. offs[v+1])`, the ids byte_to_int
+ * gives the characters of `encoding.decode([v])`), padded with pad_byte on the left (pad_left != 0) or on the right;
+ * rows with is_eot[v] != 0 (string "<|endoftext|>", :20-22) are bpt copies of eot_byte.  is_eot may be NULL.
+ * out: int16 [n_rows, bpt]. */
+int mot_ttb_build(const int16_t* chars, const int32_t* offs, const uint8_t* is_eot, int32_t n_rows, int32_t bpt,
+                  int32_t pad_left, int32_t pad_byte, int32_t eot_byte, int16_t* out, void* stream);
+
+/* The same table under another (bpt, pad side): the scaled-pre-train files ttb_{16,18,20}_{left,right}_pad.json
+ * (spt/train_gpt.py:665-672) are create_ttb of the same strings.  A row's characters are its non-pad entries in order
+ * (first min(count, bpt_out) kept, as create_ttb.py:24); all-eot rows stay all-eot.  bpt_in, bpt_out <= 32; out != table. */
+int mot_ttb_repad(const int16_t* table, int32_t n_rows, int32_t bpt_in, int32_t bpt_out, int32_t pad_left,
+                  int32_t pad_byte, int32_t eot_byte, int16_t* out, void* stream);
+
 /* uint16 shard tokens -> int32 ids on the device.  Replaces the host-side `.to(torch.int32)` of load_data_shard
  * (spt/train_gpt.py:640-648) so that the upload moves the shard's own 2 bytes per token.  Pointers 16-byte aligned. */
 int mot_tokens_widen_u16(const void* tok_u16, int64_t n, int32_t* out, void* stream);
@@ -232,6 +246,15 @@ size_t mot_pull_workspace_bytes(int64_t n_rows, int64_t tokens_per_row, int32_t 
 int mot_pull(const void* bytes_in, void* bytes_out, int64_t n_rows, int64_t tokens_per_row, int32_t bpt,
              int32_t ids_i64, int32_t pad_byte, int32_t eot_byte, int32_t from_right, void* workspace,
              size_t ws_bytes, void* stream);
+
+/* ---- output side: token rows -> byte rows (the mirror image of the input mix) ------------------------------------
+ * y[(t*bpt + k), :] = x[t, :] for k < bpt: ByteMixoutCopy's `einops.repeat(x, "... T D -> ... (T bpt) D")`
+ * (spt/train_gpt.py:493); the backward sums the bpt copies in fp32: grad_x[t] = sum_k grad_y[t*bpt + k].
+ * (ByteMixoutSplit's `rearrange "... T (bpt D) -> ... (T bpt) D"`, :516, is a view of contiguous rows: no kernel.)
+ * x / grad_x: [n_rows, dim]; y / grad_y: [n_rows*bpt, dim]; dim a multiple of 16 bytes; pointers 16-byte aligned. */
+int mot_mixout_copy_fwd(const void* x, void* y, int64_t n_rows, int32_t dim, int32_t bpt, int32_t dtype, void* stream);
+int mot_mixout_copy_bwd(const void* grad_y, void* grad_x, int64_t n_rows, int32_t dim, int32_t bpt, int32_t dtype,
+                        void* stream);
 
 /* ---- dense projection of the concat+projection variants (tcgen05 tensor cores) -------------------------------
  * dtype = MOT_BF16: bf16 operands (kind::f16); MOT_F32: fp32 operands read in place on the TF32 path (kind::tf32, the

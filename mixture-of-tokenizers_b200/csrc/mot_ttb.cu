@@ -103,6 +103,55 @@ __global__ void __launch_bounds__(256) tokens_widen_u16_kernel(const unsigned sh
   for (long long i = (groups << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
 }
 
+
+// ttb table build (modded-nanogpt/create_ttb.py:18-31) as an integer gather: row v of the table is the first
+// min(bpt, len_v) character ids of token v's string, padded on the left or on the right with `pad_byte`; a token whose
+// string is the end-of-text marker becomes bpt copies of `eot_byte` (:20-22).  The strings arrive as one flat id
+// stream `chars` with offsets `offs` [n_rows + 1] (a negative length marks an end-of-text row).  One thread per table
+// entry: out[v, k] is either a pad or ONE gathered id, so all stores are coalesced 2-byte writes of consecutive k.
+__global__ void __launch_bounds__(256) ttb_build_kernel(const short* __restrict__ chars, const int* __restrict__ offs,
+                                                       const unsigned char* __restrict__ is_eot, int n_rows, int bpt, int pad_left,
+                                                       int pad_byte, int eot_byte, short* __restrict__ out) {
+  const long long total = (long long)n_rows * bpt;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i / bpt), k = (int)(i - (long long)v * bpt);
+    int id = pad_byte;
+    if (is_eot != nullptr && is_eot[v]) {
+      id = eot_byte;
+    } else {
+      const int a = __ldg(offs + v), len = min(__ldg(offs + v + 1) - a, bpt);  // keeps the FIRST bpt characters
+      const int j = pad_left ? k - (bpt - len) : k;                            // index into the kept characters
+      if (j >= 0 && j < len) id = __ldg(chars + a + j);
+    }
+    out[i] = (short)id;
+  }
+}
+
+// Re-pad / truncate / flip the pad side of an existing table (the scaled-pre-train tables ttb_{16,18,20}_{left,right}_pad
+// are the same strings under another (bpt, pad_position), spt/train_gpt.py:665-672).  A row's characters are its non-pad
+// entries in order; rows that are all `eot_byte` stay all `eot_byte`.  One warp per row (bpt <= 32): ballot of the
+// non-pad lanes gives every character its rank, i.e. its place in the re-padded row.
+__global__ void __launch_bounds__(256) ttb_repad_kernel(const short* __restrict__ in, int n_rows, int bpt_in, int bpt_out, int pad_left,
+                                                       int pad_byte, int eot_byte, short* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_rows; v += warps) {
+    const int id = lane < bpt_in ? (int)__ldg(in + (size_t)v * bpt_in + lane) : pad_byte;
+    const unsigned live = __ballot_sync(0xffffffffu, lane < bpt_in && id != pad_byte);
+    const unsigned eot = __ballot_sync(0xffffffffu, lane >= bpt_in || id == eot_byte);
+    short* o = out + (size_t)v * bpt_out;
+    if (eot == 0xffffffffu) {
+      if (lane < bpt_out) o[lane] = (short)eot_byte;
+      continue;
+    }
+    const int n = min(__popc(live), bpt_out);           // characters kept (the first n)
+    if (lane < bpt_out) o[lane] = (short)pad_byte;
+    __syncwarp();
+    const int rank = __popc(live & ((1u << lane) - 1u));
+    if (((live >> lane) & 1u) && rank < n) o[pad_left ? bpt_out - n + rank : rank] = (short)id;
+  }
+}
+
 }  // namespace mot
 
 extern "C" int mot_tokens_widen_u16(const void* tok_u16, int64_t n, int32_t* out, void* stream) {
@@ -154,4 +203,35 @@ extern "C" int mot_ttb_expand(const int32_t* tok, int64_t n, const void* ttb, in
     case MOT_TTB_BF16: return mot::launch_expand<MOT_TTB_BF16>(tok, n, ttb, tok_vocab, bpt, out, out_i64, s);
   }
   return MOT_ERR_UNSUPPORTED;
+}
+
+extern "C" int mot_ttb_build(const int16_t* chars, const int32_t* offs, const uint8_t* is_eot, int32_t n_rows, int32_t bpt,
+                             int32_t pad_left, int32_t pad_byte, int32_t eot_byte, int16_t* out, void* stream) {
+  if (n_rows < 0 || bpt <= 0) return MOT_ERR_BAD_ARG;
+  if (n_rows == 0) return MOT_OK;
+  if (!offs || !out) return MOT_ERR_BAD_ARG;   // chars may be null when every string is empty
+  int sms = 0, optin = 0;
+  if (int rc = mot::device_props(&sms, &optin)) return rc;
+  long long blocks = ((long long)n_rows * bpt + 255) / 256;
+  if (blocks > sms * 8LL) blocks = sms * 8LL;
+  mot::ttb_build_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      chars, offs, is_eot, n_rows, bpt, pad_left, pad_byte, eot_byte, out);
+  mot::count_launch();
+  return mot::check_launch();
+}
+
+extern "C" int mot_ttb_repad(const int16_t* table, int32_t n_rows, int32_t bpt_in, int32_t bpt_out, int32_t pad_left,
+                             int32_t pad_byte, int32_t eot_byte, int16_t* out, void* stream) {
+  if (n_rows < 0 || bpt_in <= 0 || bpt_out <= 0) return MOT_ERR_BAD_ARG;
+  if (bpt_in > 32 || bpt_out > 32) return MOT_ERR_UNSUPPORTED;
+  if (n_rows == 0) return MOT_OK;
+  if (!table || !out || table == out) return MOT_ERR_BAD_ARG;
+  int sms = 0, optin = 0;
+  if (int rc = mot::device_props(&sms, &optin)) return rc;
+  long long blocks = ((long long)n_rows + 7) / 8;
+  if (blocks > sms * 8LL) blocks = sms * 8LL;
+  mot::ttb_repad_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, n_rows, bpt_in, bpt_out, pad_left, pad_byte, eot_byte, out);
+  mot::count_launch();
+  return mot::check_launch();
 }

@@ -24,10 +24,13 @@ RUN_VARIANTS = {
     "V3b": dict(combine="add", tok_norm=True, byte_norm=True, out_norm=False, slot_major=True),  # runs/73
     "V3c": dict(combine="add", tok_norm=True, byte_norm=True, out_norm=False, slot_major=True),  # runs/74 (+lambdas)
     "V3d": dict(combine="add", tok_norm=True, byte_norm=True, out_norm=True, slot_major=True),   # runs/71041 (+lambdas)
+    "V3e": dict(combine="add", tok_norm=True, byte_norm=True, out_norm=True, slot_major=True),   # runs/71042-44 (lambdas / their sum)
     "V4": dict(combine="concat"),                                                                # runs/711
     "V5": dict(combine="bytes_only"),                                                            # runs/4
 }
-_LAMBDA_VARIANTS = ("V3c", "V3d")
+_LAMBDA_VARIANTS = ("V3c", "V3d", "V3e")
+# (byte, token) initial values of the two trailing `scalars` entries per run (runs/74:259; runs/71043:252-259; runs/71044)
+LAMBDA_INIT = {"run74": (0.5, 0.5), "run71042": (0.5, 0.5), "run71043": (0.01, 0.99), "run71044": (0.4, 0.6)}
 
 
 class MoTEmbedding(nn.Module):
@@ -38,7 +41,8 @@ class MoTEmbedding(nn.Module):
     table the byte ids are derived inside the kernel (no-pull path)."""
 
     def __init__(self, token_vocab_size: int, byte_vocab_size: int, token_dim: int, byte_dim: int,
-                 bytes_per_token: int = 16, variant: str = "V3", ttb: Optional[torch.Tensor] = None):
+                 bytes_per_token: int = 16, variant: str = "V3", ttb: Optional[torch.Tensor] = None,
+                 lambda_init=(0.5, 0.5)):
         super().__init__()
         if variant not in RUN_VARIANTS:
             raise NotImplementedError(f"mot_b200: variant {variant!r} has no fused kernel")
@@ -46,7 +50,8 @@ class MoTEmbedding(nn.Module):
         self.spec = MixSpec(**RUN_VARIANTS[variant])
         self.embed_tokens = nn.Embedding(token_vocab_size, token_dim) if variant != "V5" else None
         self.embed_bytes = nn.Embedding(byte_vocab_size, byte_dim) if variant != "V0" else None
-        self.lambdas = nn.Parameter(torch.tensor([0.5, 0.5])) if variant in _LAMBDA_VARIANTS else None
+        self.lambdas = nn.Parameter(torch.tensor([float(lambda_init[0]), float(lambda_init[1])])) \
+            if variant in _LAMBDA_VARIANTS else None
         self.register_buffer("ttb", ttb, persistent=False)
         self.grad_bucket = None
 
@@ -64,6 +69,8 @@ class MoTEmbedding(nn.Module):
         lam = None
         if self.lambdas is not None:  # kernel order (tok, byte); parameter order (byte, tok) like scalars[-2], scalars[-1]
             lam = self.lambdas.flip(0)
+            if self.variant == "V3e":  # runs/71042:311-313: both scalars divided by their sum
+                lam = lam / lam.sum()
         spec = self.spec
         if byte_inputs is None and self.embed_bytes is not None:
             spec = MixSpec(**{**RUN_VARIANTS[self.variant], "slot_major": False,

@@ -262,6 +262,7 @@ class MixSpec:
     proj:      None | "linear" -> F.linear(mix, W[, bias]) applied before out_norm
     bytes_first: concat order [bytes | tok] (mathblations) instead of [tok | bytes]
     byte_fc:   V3f: project the concatenated bytes with W before the add
+    lam_over_sum: V3e: both lambdas are divided by their sum (runs/71042:311-313)
     """
     combine: str = "add"
     tok_norm: bool = False
@@ -270,6 +271,7 @@ class MixSpec:
     proj: Optional[str] = None
     bytes_first: bool = False
     byte_fc: bool = False
+    lam_over_sum: bool = False
 
 
 # name -> (spec, reference citation)
@@ -281,6 +283,7 @@ VARIANTS = {
     "V3b": (MixSpec(combine="add", tok_norm=True, byte_norm=True, out_norm=False), "runs/73:229-231,313-315"),
     "V3c": (MixSpec(combine="add", tok_norm=True, byte_norm=True, out_norm=False), "runs/74:314-316 (+lambdas)"),
     "V3d": (MixSpec(combine="add", tok_norm=True, byte_norm=True, out_norm=True), "runs/71041:226-228,311-313 (+lambdas)"),
+    "V3e": (MixSpec(combine="add", tok_norm=True, byte_norm=True, out_norm=True, lam_over_sum=True), "runs/71042:225-228,311-314 (+lambdas / their sum)"),
     "V3f": (MixSpec(combine="add", byte_fc=True), "runs/71051:226-229,312-314"),
     "V4": (MixSpec(combine="concat"), "runs/711:224-232,314-316"),
     "V5": (MixSpec(combine="bytes_only"), "runs/4_bytes-in_toks-valemb.py:226-232,313"),
@@ -323,6 +326,9 @@ def mot_embed_forward(spec: MixSpec, tokens: torch.Tensor, byte_ids: Optional[to
     """
     tokens = tokens.reshape(-1).long()
     n_pos = tokens.numel()
+    if spec.lam_over_sum:  # runs/71042:311: norm_scalrs_sum = scalars[-1] + scalars[-2]
+        lam_sum = lam_tok + lam_byte
+        lam_tok, lam_byte = lam_tok / lam_sum, lam_byte / lam_sum
     t = None
     if spec.combine != "bytes_only":
         t = F.embedding(tokens, E_tok)
