@@ -278,6 +278,13 @@ int mot_linear_bwd_input(const void* dy, const void* w, void* dx, int64_t n_toke
 int mot_linear_bwd_weight(const void* dy, const void* x, float* dw_f32, void* dw_bf16, int64_t n_tokens, int32_t in_dim,
                           int32_t out_dim, int32_t dtype, void* workspace, size_t ws_bytes, void* stream);
 
+/* fp32 -> bf16, round to nearest even: CastedLinear's per-call `self.weight.type_as(x)` (spt/train_gpt.py:185-186) for the
+ * fp32 master weight of the mixin projection.  Pointers 16-byte aligned. */
+int mot_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* out[dim] (fp32) = column sums of x [n_rows, dim] (bf16 or fp32): the bias gradient of F.linear
+ * (mathblations/model.py:261,268).  Fixed summation order (no atomics).  dim even. */
+int mot_colsum(const void* x, float* out, int64_t n_rows, int32_t dim, int32_t dtype, void* stream);
+
 /* Row-wise rms_norm without weight (F.rms_norm(x, (x.size(-1),)), spt/train_gpt.py:172-173) over [n_rows, dim] and
  * its backward dy = rs*g - y*rs^3*mean(g.y): the `norm(...)` around the projection (runs/7:234, train_gpt.py:443). */
 int mot_rmsnorm_fwd(const void* y, void* out, int64_t n_rows, int32_t dim, int32_t dtype, float eps, void* stream);

@@ -132,7 +132,15 @@ static int validate(const MotDesc* d) {
     case MOT_BYTES_ONLY: if (d->out_dim != db) return MOT_ERR_BAD_ARG; break;
     case MOT_MEAN: if (d->byte_dim != d->tok_dim || d->out_dim != d->tok_dim) return MOT_ERR_BAD_ARG; break;
   }
-  if (d->out_dim > 8 * 32 * 8) return MOT_ERR_UNSUPPORTED;  // CPL <= 8
+  // a lane holds at most 8 chunks of 8 elements per launch: 2048 columns.  A concat without a norm over the whole row
+  // runs as two launches (concat_splits), so the cap applies to each half: the widest reference operand
+  // (spt/experiments100_000steps.sh: 1024 + 16 x 128 = 3072 columns) fits.
+  constexpr int kMaxCols = 8 * 32 * 8;
+  if (d->combine == MOT_CONCAT && !(d->flags & (MOT_F_OUT_NORM | MOT_F_HAS_LAMBDAS))) {
+    if (d->tok_dim > kMaxCols || db > kMaxCols) return MOT_ERR_UNSUPPORTED;
+  } else if (d->out_dim > kMaxCols) {
+    return MOT_ERR_UNSUPPORTED;
+  }
   if (d->row_stride != 0 || d->col_offset != 0) {  // a column slice of wider rows
     const long long ld = d->row_stride ? d->row_stride : d->out_dim;
     if (d->col_offset < 0 || ld < (long long)d->col_offset + d->out_dim || ld > 0x7fffffffLL) return MOT_ERR_BAD_ARG;

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "mot_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "mot_linear_bwd_input": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
     "mot_linear_bwd_weight": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
+    "mot_cast_f32_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "mot_colsum": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mot_rmsnorm_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P]),
     "mot_rmsnorm_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P]),
 }

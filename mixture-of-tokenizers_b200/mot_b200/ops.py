@@ -79,18 +79,8 @@ class _on_device:
         return False
 
 
-def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
-    """tokens_to_bytes (spt/data_creation.py:61-67): [B,T] -> [B, T*bpt], [T] -> [1, T*bpt].
-
-    `ttb` is the [V, bpt] table: int16 (native) or the reference's float containers (fp32
-    nn.Embedding weight, or the bf16-cast weight of the runs with its id-rounding quirk)."""
-    dev = _require_cuda(tokens, ttb)
-    if ttb.dtype not in _TTB_DTYPE or ttb.dim() != 2:
-        raise NotImplementedError(f"mot_b200.ttb_expand: ttb must be a 2-D int16/float32/bfloat16 table, got {ttb.dtype}")
-    if out_dtype not in (torch.int64, torch.int32):
-        raise NotImplementedError("mot_b200.ttb_expand: out_dtype must be int64 or int32")
-    tok = tokens.to(torch.int32).contiguous()
-    ttb = ttb.contiguous()
+def _ttb_expand_impl(tok: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    dev = tok.device
     V, bpt = ttb.shape
     n = tok.numel()
     out = torch.empty((n, bpt), dtype=out_dtype, device=dev)
@@ -98,35 +88,58 @@ def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype =
         rc = L.lib().mot_ttb_expand(_ptr(tok), n, _ptr(ttb), V, bpt, _TTB_DTYPE[ttb.dtype], _ptr(out),
                                     1 if out_dtype == torch.int64 else 0, _stream(dev))
     L.check(rc, "mot_ttb_expand")
+    return out
+
+
+def ttb_expand(tokens: torch.Tensor, ttb: torch.Tensor, out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """tokens_to_bytes (spt/data_creation.py:61-67): [B,T] -> [B, T*bpt], [T] -> [1, T*bpt].
+
+    `ttb` is the [V, bpt] table: int16 (native) or the reference's float containers (fp32
+    nn.Embedding weight, or the bf16-cast weight of the runs with its id-rounding quirk)."""
+    _require_cuda(tokens, ttb)
+    if ttb.dtype not in _TTB_DTYPE or ttb.dim() != 2:
+        raise NotImplementedError(f"mot_b200.ttb_expand: ttb must be a 2-D int16/float32/bfloat16 table, got {ttb.dtype}")
+    if out_dtype not in (torch.int64, torch.int32):
+        raise NotImplementedError("mot_b200.ttb_expand: out_dtype must be int64 or int32")
+    tok = tokens.to(torch.int32).contiguous().reshape(-1)
+    ttb = ttb.contiguous()
+    if _custom_ops_wanted():
+        out = torch.ops.mot_b200.ttb_expand(tok, ttb, out_dtype == torch.int64)
+    else:
+        out = _ttb_expand_impl(tok, ttb, out_dtype)
     if tokens.dim() == 2:
         return out.view(tokens.shape[0], -1)
     return out.view(1, -1)
 
 
-def tokens_to_digits(tokens: torch.Tensor, max_digits_per_token: int, op_token: int, eq_token: int, pad_token: int,
-                     out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
-    """GenerateEquations.tokens_to_digits (mathblations/data.py:92-109) on the device: [n] -> [n * dpt]."""
-    dev = _require_cuda(tokens)
-    if tokens.dtype not in (torch.int32, torch.int64) or out_dtype not in (torch.int32, torch.int64):
-        raise NotImplementedError("mot_b200.tokens_to_digits: int32 / int64 only")
-    t = tokens.reshape(-1).contiguous()
-    out = torch.empty(t.numel() * max_digits_per_token, dtype=out_dtype, device=dev)
+def _tokens_to_digits_impl(t: torch.Tensor, dpt: int, op_token: int, eq_token: int, pad_token: int,
+                           out_dtype: torch.dtype) -> torch.Tensor:
+    dev = t.device
+    out = torch.empty(t.numel() * dpt, dtype=out_dtype, device=dev)
     with _on_device(dev):
-        rc = L.lib().mot_tokens_to_digits(_ptr(t), t.numel(), 1 if t.dtype == torch.int64 else 0, max_digits_per_token,
+        rc = L.lib().mot_tokens_to_digits(_ptr(t), t.numel(), 1 if t.dtype == torch.int64 else 0, dpt,
                                           op_token, eq_token, pad_token, _ptr(out), 1 if out_dtype == torch.int64 else 0,
                                           _stream(dev))
     L.check(rc, "mot_tokens_to_digits")
     return out
 
 
-def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_byte: int, from_right: bool) -> torch.Tensor:
-    dev = _require_cuda(byte_tensor)
-    if byte_tensor.dtype not in (torch.int32, torch.int64) or byte_tensor.dim() != 2:
-        raise NotImplementedError("mot_b200.pull: byte_tensor must be a 2-D int32 / int64 tensor [B, T*bpt]")
-    B, TB = byte_tensor.shape
-    if TB % bytes_per_token:
-        raise RuntimeError("T must be divisible by bytes_per_token")   # the reference's assert (data_creation.py:189)
-    x = byte_tensor.contiguous()
+def tokens_to_digits(tokens: torch.Tensor, max_digits_per_token: int, op_token: int, eq_token: int, pad_token: int,
+                     out_dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """GenerateEquations.tokens_to_digits (mathblations/data.py:92-109) on the device: [n] -> [n * dpt]."""
+    _require_cuda(tokens)
+    if tokens.dtype not in (torch.int32, torch.int64) or out_dtype not in (torch.int32, torch.int64):
+        raise NotImplementedError("mot_b200.tokens_to_digits: int32 / int64 only")
+    t = tokens.reshape(-1).contiguous()
+    if _custom_ops_wanted():
+        return torch.ops.mot_b200.tokens_to_digits(t, max_digits_per_token, op_token, eq_token, pad_token,
+                                                   out_dtype == torch.int64)
+    return _tokens_to_digits_impl(t, max_digits_per_token, op_token, eq_token, pad_token, out_dtype)
+
+
+def _pull_impl(x: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_byte: int, from_right: bool) -> torch.Tensor:
+    dev = x.device
+    B, TB = x.shape
     out = torch.empty_like(x)
     T = TB // bytes_per_token
     if B * T == 0:
@@ -137,6 +150,18 @@ def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_by
                               eot_byte, 1 if from_right else 0, _ptr(ws), ws.numel(), _stream(dev))
     L.check(rc, "mot_pull")
     return out
+
+
+def _pull(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int, eot_byte: int, from_right: bool) -> torch.Tensor:
+    _require_cuda(byte_tensor)
+    if byte_tensor.dtype not in (torch.int32, torch.int64) or byte_tensor.dim() != 2:
+        raise NotImplementedError("mot_b200.pull: byte_tensor must be a 2-D int32 / int64 tensor [B, T*bpt]")
+    if byte_tensor.shape[1] % bytes_per_token:
+        raise RuntimeError("T must be divisible by bytes_per_token")   # the reference's assert (data_creation.py:189)
+    x = byte_tensor.contiguous()
+    if _custom_ops_wanted():
+        return torch.ops.mot_b200.pull(x, bytes_per_token, pad_byte, eot_byte, from_right)
+    return _pull_impl(x, bytes_per_token, pad_byte, eot_byte, from_right)
 
 
 def pull_from_left(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: int = 456, eot_byte: int = 457) -> torch.Tensor:
@@ -286,8 +311,9 @@ _SIDE_STREAMS: dict = {}
 
 
 def acquire_workspace(desc: L.MotDesc, dev) -> Workspace:
-    # the zeroed head of the workspace is laid out by (tok_vocab, byte_vocab, byte_dim): one pool per geometry
-    key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine)
+    # the zeroed head of the workspace (histogram | byte accumulators | one fp32 slot per stream chunk) is laid out by the
+    # table geometry AND by (n_tokens, tok_dim): a buffer is only "clean" for the exact layout it was last used with
+    key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine, desc.n_tokens, desc.tok_dim)
     free = _WS_POOL.get(key)
     if free is None:
         free = _WS_POOL[key] = []
@@ -320,6 +346,13 @@ def embed_plan_async(desc: L.MotDesc, tok, ws: Workspace, dev, stream: Optional[
                                           ws.ev_fork.cuda_event, ws.ev_join.cuda_event)
     L.check(rc, "mot_embed_plan_async")
     ws.pending = True
+
+
+def embed_plan_join_if_capturing(ws: Optional[Workspace], dev, stream: Optional[int] = None) -> None:
+    """Inside a CUDA-graph capture (torch.cuda.graph / make_graphed_callables) the side stream must rejoin before the
+    capture of the forward ends; the graph keeps plan and forward concurrent.  Called by every forward that forked."""
+    if ws is not None and ws.pending and torch.cuda.is_current_stream_capturing():
+        embed_plan_join(ws, dev, stream)
 
 
 def embed_plan_join(ws: Workspace, dev, stream: Optional[int] = None) -> None:
@@ -367,10 +400,7 @@ class _MotEmbedFn(torch.autograd.Function):
         keep = needs_grad and n > 0 and bool(L.lib().mot_embed_bwd_uses_saved(desc))
         rstd = torch.empty(n, dtype=torch.float32, device=dev) if keep else None
         embed_forward_out(desc, tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out, st, rstd=rstd)
-        if ctx.ws is not None and torch.cuda.is_current_stream_capturing():
-            # CUDA-graph capture (torch.cuda.graph / make_graphed_callables): the side stream must rejoin before the
-            # capture of the forward ends; the graph keeps plan and forward concurrent
-            embed_plan_join(ctx.ws, dev, st)
+        embed_plan_join_if_capturing(ctx.ws, dev, st)
         ctx.desc, ctx.dev = desc, dev
         saved = (tok, ids, ttb, E_tok_c, E_byte_c, lam_c, out if keep else None, rstd)
         ctx.save_for_backward(*[t if t is not None else _ABSENT for t in saved])
@@ -393,6 +423,11 @@ class _MotEmbedFn(torch.autograd.Function):
             # parameter the normal path is taken and autograd adds to it.
             for i, (pv, E) in enumerate(zip(ctx.grad_bufs, (E_tok, E_byte))):
                 if pv is not None and E is not None and pv[0].grad is None:
+                    view = pv[1]
+                    if view.dtype != E.dtype or view.shape != E.shape or not view.is_contiguous() or view.device != E.device:
+                        raise TypeError("mot_b200: the gradient-bucket view of a table must match its dtype, shape and "
+                                        f"device and be contiguous (table {tuple(E.shape)} {E.dtype}, view "
+                                        f"{tuple(view.shape)} {view.dtype})")
                     direct[i] = pv
         gE_tok = direct[0][1] if direct[0] is not None else (torch.empty_like(E_tok) if E_tok is not None else None)
         gE_byte = direct[1][1] if direct[1] is not None else (torch.empty_like(E_byte) if E_byte is not None else None)
@@ -431,6 +466,8 @@ def mot_embed(tokens: Optional[torch.Tensor], byte_ids: Optional[torch.Tensor], 
     inside the kernel.  lam = float tensor [2] = (lam_tok, lam_byte) or None.  grad_bufs = optional
     ((param, view), (param, view)) pairs for the token / byte table: the backward writes the dense gradient into `view`
     (a slice of a dp.GradBucket) and installs it as `param.grad`."""
+    if grad_bufs is None and _custom_ops_wanted():
+        return _embed_via_custom_op(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam)
     return _MotEmbedFn.apply(spec, bpt, seq_len, tokens, byte_ids, ttb, E_tok, E_byte, lam, grad_bufs)
 
 
@@ -467,6 +504,7 @@ class _TokGatherFn(torch.autograd.Function):
             out = torch.empty((n, shape[1]), dtype=dtype, device=dev)
             embed_forward_out(desc, tok, None, None, E, None, None, out, st)
             outs.append(out)
+        embed_plan_join_if_capturing(ctx.ws, dev, st)
         ctx.desc, ctx.dev, ctx.n_tables = desc, dev, len(Es)
         ctx.save_for_backward(tok, *Es)
         return tuple(outs)
@@ -480,7 +518,8 @@ class _TokGatherFn(torch.autograd.Function):
         if ws is None:
             ws = acquire_workspace(desc, dev)
         if planned:
-            embed_plan_join(ws, dev, st)
+            if ws.pending:
+                embed_plan_join(ws, dev, st)
             clean = True
         else:
             clean, ws.clean = ws.clean, False
@@ -504,6 +543,8 @@ class _TokGatherFn(torch.autograd.Function):
 def tok_gather(tokens: torch.Tensor, *tables: torch.Tensor):
     """`[E(tokens) for E in tables]` (the value embeddings of runs/7:308 / spt/train_gpt.py:600): returns a tuple of
     [n_tokens, D] tensors; dense gradients, one token sort shared by every table."""
+    if _custom_ops_wanted():
+        return _tok_gather_via_custom_op(tokens, tables)
     return _TokGatherFn.apply(tokens, *tables)
 
 
@@ -600,6 +641,82 @@ def byte_pair_backward_out(ids_a, ids_b, bpt: int, E_byte, grad_rows, col_offset
     L.check(rc, "mot_byte_pair_bwd")
 
 
+def cast_out(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """CastedLinear's per-call `self.weight.type_as(x)` (spt/train_gpt.py:185-186) inside the library: fp32 -> bf16
+    (mot_cast_f32_bf16).  Same dtype: returned as is."""
+    w = w.detach()
+    if w.dtype == dtype:
+        return w.contiguous()
+    if w.dtype != torch.float32 or dtype != torch.bfloat16:
+        raise NotImplementedError(f"mot_b200: projection weight {w.dtype} with {dtype} tables is not supported "
+                                  "(bf16 weight, or fp32 master weight cast to bf16 per call)")
+    dev = _require_cuda(w)
+    w = w.contiguous()
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=dev)
+    with _on_device(dev):
+        rc = L.lib().mot_cast_f32_bf16(_ptr(w), _ptr(out), w.numel(), _stream(dev))
+    L.check(rc, "mot_cast_f32_bf16")
+    return out
+
+
+def colsum_out(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of x [n, dim]: the bias gradient of F.linear (mot_colsum, fixed summation order)."""
+    dev = _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        rc = L.lib().mot_colsum(_ptr(x), _ptr(out), x.shape[0], x.shape[1], _DTYPE[x.dtype], _stream(dev))
+    L.check(rc, "mot_colsum")
+    return out
+
+
+def _mixout_copy_impl(x: torch.Tensor, bpt: int, backward: bool) -> torch.Tensor:
+    dev = x.device
+    rows, D = x.shape
+    n = rows // bpt if backward else rows
+    out = torch.empty((n if backward else n * bpt, D), dtype=x.dtype, device=dev)
+    with _on_device(dev):
+        fn = L.lib().mot_mixout_copy_bwd if backward else L.lib().mot_mixout_copy_fwd
+        rc = fn(_ptr(x), _ptr(out), n, D, bpt, _DTYPE[x.dtype], _stream(dev))
+    L.check(rc, "mot_mixout_copy_bwd" if backward else "mot_mixout_copy_fwd")
+    return out
+
+
+class _MixoutCopyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, bpt):
+        ctx.bpt = bpt
+        return _mixout_copy_impl(x2d, bpt, backward=False)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _mixout_copy_impl(g.contiguous(), ctx.bpt, backward=True), None
+
+
+def mixout_copy(x: torch.Tensor, bytes_per_token: int) -> torch.Tensor:
+    """ByteMixoutCopy's expand (spt/train_gpt.py:493): `einops.repeat(x, "... T D -> ... (T bpt) D")`; the backward sums
+    the bpt copies of every row in fp32."""
+    _require_cuda(x)
+    if x.dtype not in _DTYPE:
+        raise NotImplementedError(f"mot_b200.mixout_copy: dtype {x.dtype} is not supported (bf16 / fp32 only)")
+    lead, T, D = x.shape[:-2], x.shape[-2], x.shape[-1]
+    x2 = x.contiguous().view(-1, D)
+    if _custom_ops_wanted():
+        y = torch.ops.mot_b200.mixout_copy(x2, bytes_per_token)
+    else:
+        y = _MixoutCopyFn.apply(x2, bytes_per_token)
+    return y.view(*lead, T * bytes_per_token, D)
+
+
+def mixout_split(x: torch.Tensor, bytes_per_token: int) -> torch.Tensor:
+    """ByteMixoutSplit's expand (spt/train_gpt.py:516): `rearrange(x, "... T (bpt D) -> ... (T bpt) D")` is a view of
+    contiguous rows: no kernel, no copy."""
+    lead, T, D = x.shape[:-2], x.shape[-2], x.shape[-1]
+    if D % bytes_per_token:
+        raise RuntimeError("model_dim must be divisible by bytes_per_token")   # spt/train_gpt.py:502
+    return x.contiguous().view(*lead, T * bytes_per_token, D // bytes_per_token)
+
+
 class _MotEmbedProjFn(torch.autograd.Function):
     """out = f_out( [tok | bytes] . W^T + bias ): the fused gather builds the [n, K] operand (mot_embed_fwd, CONCAT),
     the projection runs on the tensor cores (mot_linear_fwd), the row norm after it is a separate HBM-bound pass over
@@ -642,7 +759,7 @@ class _MotEmbedProjFn(torch.autograd.Function):
         Do = W.shape[0]
         if W.shape[1] != K:
             raise RuntimeError(f"mot_b200: projection weight is {tuple(W.shape)}, expected [{Do}, {K}]")
-        w16 = W.detach().to(cdt).contiguous()                  # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
+        w16 = cast_out(W, cdt)                                 # CastedLinear: W.type_as(x) (spt/train_gpt.py:186)
         ctx.ws = None
         if any(ctx.needs_input_grad[4:6]) and n > 0:
             ctx.ws = acquire_workspace(desc, dev)
@@ -654,7 +771,9 @@ class _MotEmbedProjFn(torch.autograd.Function):
             embed_forward_out(desc, tok, None, None, E_tok_c, None, None, A)
             byte_pair_forward_out(ids, ids2, bpt, E_byte_c, A, E_tok_c.shape[1], spec.eps)
         Y = torch.empty((n, Do), dtype=cdt, device=dev)
-        b32 = bias.detach().float().contiguous() if bias is not None else None
+        if bias is not None and bias.dtype != torch.float32:
+            raise NotImplementedError("mot_b200: the projection bias must be fp32 (mathblations/model.py:261)")
+        b32 = bias.detach().contiguous() if bias is not None else None
         linear_forward_out(A, w16, Y, b32)
         del A
         if spec.out_norm:
@@ -662,6 +781,7 @@ class _MotEmbedProjFn(torch.autograd.Function):
             rmsnorm_forward_out(Y, out, spec.eps)
         else:
             out = Y
+        embed_plan_join_if_capturing(ctx.ws, dev)
         ctx.desc, ctx.dev, ctx.spec = desc, dev, spec
         ctx.w_dtype, ctx.has_bias = W.dtype, bias is not None
         ctx.pair, ctx.bpt, ctx.K = ids2 is not None, bpt, K
@@ -680,7 +800,7 @@ class _MotEmbedProjFn(torch.autograd.Function):
             rmsnorm_backward_out(Y, g, dY, spec.eps)
         else:
             dY = g
-        g_bias = dY.float().sum(0) if ctx.has_bias else None
+        g_bias = colsum_out(dY) if ctx.has_bias else None
         A = torch.empty((n, K), dtype=cdt, device=dev)
         if not ctx.pair:
             embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)   # gathered again, not kept
@@ -697,7 +817,8 @@ class _MotEmbedProjFn(torch.autograd.Function):
         if ws is None:
             ws = acquire_workspace(desc, dev)
         if planned:
-            embed_plan_join(ws, dev)
+            if ws.pending:
+                embed_plan_join(ws, dev)
             clean = True
         else:
             clean, ws.clean = ws.clean, False
@@ -711,9 +832,8 @@ class _MotEmbedProjFn(torch.autograd.Function):
         ws.clean = True
         ctx.ws = None
         release_workspace(ws)
-        gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
-        return (None, None, None, None, gE_tok, gE_byte, gW, (g_bias.to(torch.float32) if g_bias is not None else None),
-                None)
+        gW = dW16 if dW16 is not None else dW32          # cast_out admits bf16 or fp32 weights only
+        return (None, None, None, None, gE_tok, gE_byte, gW, g_bias, None)
 
 
 class _MotEmbedByteFcFn(torch.autograd.Function):
@@ -739,7 +859,7 @@ class _MotEmbedByteFcFn(torch.autograd.Function):
         D = E_tok_c.shape[1]
         if ids.numel() != n * bpt or bpt * E_byte_c.shape[1] != D or tuple(W.shape) != (D, D):
             raise RuntimeError("mot_b200: byte-FC mix needs bpt*byte_dim == token_dim and a square [D, D] weight")
-        w16 = W.detach().to(cdt).contiguous()
+        w16 = cast_out(W, cdt)
         desc_b = make_desc(spec_b, n, None, E_byte_c, bpt, ids=ids, ttb=None, has_lam=False)
         desc_t = make_desc(MixSpec(combine="tok_only", out_norm=True, eps=eps), n, E_tok_c, None, 0, ids=None, ttb=None,
                            has_lam=False)
@@ -755,6 +875,7 @@ class _MotEmbedByteFcFn(torch.autograd.Function):
         out = torch.empty((n, D), dtype=cdt, device=dev)
         if n > 0:
             embed_forward_out(desc_t, tok, None, None, E_tok_c, None, None, out, addend=Y)
+        embed_plan_join_if_capturing(ctx.ws, dev)
         ctx.desc_b, ctx.desc_t, ctx.dev, ctx.w_dtype = desc_b, desc_t, dev, W.dtype
         ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y)
         return out
@@ -772,7 +893,8 @@ class _MotEmbedByteFcFn(torch.autograd.Function):
         if ws is None:
             ws = acquire_workspace(desc_t, dev)
         if planned:
-            embed_plan_join(ws, dev)
+            if ws.pending:
+                embed_plan_join(ws, dev)
             clean = True
         else:
             clean, ws.clean = ws.clean, False
@@ -793,7 +915,7 @@ class _MotEmbedByteFcFn(torch.autograd.Function):
                            plan_ready=False, ws_clean=clean_b)
         wsb.clean = True
         release_workspace(wsb)
-        gW = dW16 if dW16 is not None else dW32.to(ctx.w_dtype)
+        gW = dW16 if dW16 is not None else dW32
         return None, None, None, None, None, gE_tok, gE_byte, gW
 
 
@@ -801,6 +923,8 @@ def mot_embed_byte_fc(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch
                       W_fc: torch.Tensor, *, bpt: int = 16, slot_major: bool = True, eps: float = FP32_EPS) -> torch.Tensor:
     """`norm(token_embs + F.linear(cat(byte_embs), byte_fc))` (runs/71051:226-229,312-314): [n_tokens, D]."""
     spec_b = MixSpec(combine="bytes_only", out_norm=False, slot_major=slot_major, eps=eps)
+    if _custom_ops_wanted():
+        return _byte_fc_via_custom_op(spec_b, bpt, eps, tokens, byte_ids, E_tok, E_byte, W_fc)
     return _MotEmbedByteFcFn.apply(spec_b, bpt, eps, tokens, byte_ids, E_tok, E_byte, W_fc)
 
 
@@ -813,6 +937,8 @@ def mot_embed_proj(tokens: torch.Tensor, byte_ids: torch.Tensor, E_tok: torch.Te
     call, gradient returned in fp32); or everything fp32 (mathblations: TF32 tensor cores).  byte_ids2: the second id
     tensor of `--add-padded-and-pulled` (spt/train_gpt.py:371-379), rows summed before the per-byte norm.  Returns
     [n_tokens, W.shape[0]] in the table dtype."""
+    if _custom_ops_wanted():
+        return _proj_via_custom_op(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2)
     return _MotEmbedProjFn.apply(spec, bpt, tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2)
 
 
@@ -822,3 +948,9 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     L.lib().mot_launch_count_reset()
+
+
+# torch.library registration of the same entry points (torch.compile / compiled autograd see opaque operators)
+from ._library import (custom_ops_wanted as _custom_ops_wanted, set_custom_ops,  # noqa: E402,F401
+                       embed_via_custom_op as _embed_via_custom_op, tok_gather_via_custom_op as _tok_gather_via_custom_op,
+                       proj_via_custom_op as _proj_via_custom_op, byte_fc_via_custom_op as _byte_fc_via_custom_op)
