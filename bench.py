@@ -318,7 +318,8 @@ def run_ours(args):
         ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out, rstd=rstd)
         ops.embed_plan_join(ws, dev)
         ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf,
-                               plan_ready=True, ws_clean=True, out_saved=out if rstd is not None else None, rstd=rstd)
+                               plan_ready=True, ws_clean=True, out_saved=out if rstd is not None else None, rstd=rstd,
+                               plan_joined=True)
         ws.clean = True
         if world > 1:
             bucket.all_reduce_avg()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MOT_B200_ABI_VERSION 3
+#define MOT_B200_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------- */
 enum {
@@ -92,7 +92,8 @@ typedef struct MotDesc {
                           With col_offset it lets a call produce or consume a column slice of wider rows, e.g. the
                           token half of the [tok | bytes] operand next to mot_byte_pair_fwd's byte half. */
   int32_t col_offset;  /* first column of this call's slice inside those rows (multiple of 8) */
-  int32_t reserved;    /* 0 */
+  int32_t dp_slabs;    /* 0 / 1: the backward runs in one piece.  n > 1: the caller will run it as n vocabulary slabs
+                          (mot_embed_bwd_slab); only sizes the workspace (one fp32 slot per finer stream chunk) */
 } MotDesc;
 
 const char* mot_strerror(int rc);
@@ -105,6 +106,11 @@ void mot_launch_count_reset(void);
 /* Measurement hook (bench.py): cudaEvent_t pairs recorded on the launch stream immediately around the
  * main forward kernel and the main backward kernel of the following calls; NULL disables a pair. */
 void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_start, void* bwd_stop);
+
+/* Measurement hook (tools/trace_timeline.py): a device buffer of 64 x int64 per warp of the main forward / backward kernel
+ * that receives %globaltimer stamps of the warp's phases.  Only libraries built with -DMOT_TRACE write it (the shipped
+ * build compiles the stamps out); NULL disables. */
+void mot_profile_trace(void* device_buffer);
 
 /* tokens -> padded byte ids.
  * Replaces tokens_to_bytes (spt/data_creation.py:61-67, runs/7:444-450): gather ttb rows
@@ -144,8 +150,13 @@ size_t mot_embed_workspace_bytes(const MotDesc* d);
  *   MOT_WS_CLEAN      : the head of the workspace (histogram, byte-gradient accumulators) is all zero, which is the
  *                       state mot_embed_workspace_init() and every completed mot_embed_bwd() leave it in; a caller
  *                       that keeps one workspace per stream passes it from the second step on and saves a memset.
- *                       Without the flag the library clears what it needs itself. */
-enum { MOT_WS_PLAN_READY = 1, MOT_WS_CLEAN = 2 };
+ *                       Without the flag the library clears what it needs itself.
+ *   MOT_WS_PLAN_JOINED: (with MOT_WS_PLAN_READY) the plan ran on ANOTHER stream and this stream waited for its event
+ *                       (mot_embed_plan_async + mot_stream_wait_event), i.e. it was complete before this call's kernels were
+ *                       launched: the backward may then read the plan before its programmatic-launch wait, while the
+ *                       previous kernel of this stream is still draining.  Never pass it when mot_embed_plan() ran on the
+ *                       same stream right before the backward. */
+enum { MOT_WS_PLAN_READY = 1, MOT_WS_CLEAN = 2, MOT_WS_PLAN_JOINED = 4 };
 int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_t ws_bytes, void* stream);
 
 /* Fused forward: out[n_tokens, out_dim] =
@@ -204,6 +215,21 @@ int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids,
                      const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
                      void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes, int32_t ws_flags,
                      void* stream);
+
+/* The backward as `n_slabs` vocabulary slabs, so that the data-parallel exchange of slab k (mot_dp_exchange on a second
+ * stream) runs beside the backward of slab k + 1 -- the overlap the reference gets from its asynchronous per-parameter
+ * all-reduces (runs/7:697-711).  Call k = 0 .. n_slabs - 1 in order with the same arguments: call k writes rows
+ * [row_lo, row_hi) = mot_embed_slab_rows(tok_vocab, k, n_slabs) of gE_tok (final when the call's kernels have run);
+ * gE_byte and g_lam are final after the last call.  d->dp_slabs must equal n_slabs (workspace layout); calls k > 0 need
+ * MOT_WS_PLAN_READY.  reserve_sms (0..16): SMs the launch leaves free for a concurrently running exchange kernel.
+ * Only where mot_embed_bwd_uses_saved(d) holds (the MoT-sum variant with out_saved / rstd_saved); MOT_ERR_UNSUPPORTED
+ * otherwise -- run mot_embed_bwd_ex and one exchange instead. */
+int mot_embed_bwd_slab(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                       const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                       const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte, float* g_lam,
+                       void* workspace, size_t ws_bytes, int32_t ws_flags, int32_t slab, int32_t n_slabs,
+                       int32_t reserve_sms, void* stream);
+int mot_embed_slab_rows(int32_t tok_vocab, int32_t slab, int32_t n_slabs, int32_t* row_lo, int32_t* row_hi);
 
 /* 1 when mot_embed_bwd_ex would use out_saved / rstd_saved for this descriptor (so a caller knows whether keeping
  * them pays), else 0: only the MoT-sum variant, widths 512 / 768 / 1024, and at most 4 positions per vocabulary row

@@ -8,6 +8,7 @@ namespace mot {
 
 thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 static std::atomic<long long> g_launches{0};
+long long* g_trace = nullptr;
 cudaEvent_t g_prof_fwd_start = nullptr, g_prof_fwd_stop = nullptr, g_prof_start = nullptr, g_prof_stop = nullptr;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -77,3 +78,5 @@ extern "C" void mot_profile_events(void* fwd_start, void* fwd_stop, void* bwd_st
   mot::g_prof_start = reinterpret_cast<cudaEvent_t>(bwd_start);
   mot::g_prof_stop = reinterpret_cast<cudaEvent_t>(bwd_stop);
 }
+
+extern "C" void mot_profile_trace(void* device_buffer) { mot::g_trace = reinterpret_cast<long long*>(device_buffer); }

@@ -18,6 +18,7 @@ void count_launch(int n = 1);
 int check_launch();  // cudaGetLastError -> MOT_OK / MOT_ERR_CUDA
 int device_props(int* sm_count, int* smem_optin);
 // optional event pairs recorded around the main forward / backward kernel (mot_profile_events)
+extern long long* g_trace;  // device buffer for per-warp time stamps (mot_profile_trace; only libraries built with -DMOT_TRACE write it)
 extern cudaEvent_t g_prof_fwd_start, g_prof_fwd_stop, g_prof_start, g_prof_stop;
 
 // Launch with programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor in the stream
@@ -40,6 +41,19 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 // ---------------------------------------------------------------- device side
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// per-warp time stamps for the timeline experiments (tools/trace_*.py): 64 slots of 8 bytes per warp
+#ifdef MOT_TRACE
+#define MOT_STAMP(buf, gw, slot)                                                                      \
+  do {                                                                                               \
+    if ((buf) != nullptr && (threadIdx.x & 31) == 0 && (slot) < 64) {                                 \
+      unsigned long long t_;                                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      (buf)[(size_t)(gw) * 64 + (slot)] = (long long)t_;                                             \
+    }                                                                                                \
+  } while (0)
+#else
+#define MOT_STAMP(buf, gw, slot) do { } while (0)
+#endif
 // PDL: let the next kernel in the stream start launching / block until every predecessor grid has completed and its
 // memory is visible.  Both are no-ops when the kernel was launched without the PDL attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -109,6 +109,20 @@ static int stream_chunk(long long n_tokens, int warps_per_cta) {
   return (int)R;
 }
 
+// Chunk size when the backward runs as `n_slabs` vocabulary slabs beside the gradient exchange (mot_embed_bwd_slab): one
+// chunk per warp of a launch that leaves up to 16 SMs to the exchange kernel, for a slab holding 1 / n_slabs of the
+// stream (uniform token ids; a slab with more entries walks several chunks per warp).  A pure function of
+// (n_tokens, n_slabs): the workspace layout depends on it.
+constexpr int kDpReserveMax = 16;
+static int stream_chunk_slab(long long n_tokens, int n_slabs, int warps_per_cta) {
+  const long long warps = (148LL - kDpReserveMax) * warps_per_cta;
+  const long long per_slab = (n_tokens + n_slabs - 1) / n_slabs;
+  long long R = (per_slab + warps - 1) / warps;
+  if (R < 1) R = 1;
+  if (R > 32) R = (R + 31) / 32 * 32;
+  return (int)R;
+}
+
 static int validate(const MotDesc* d) {
   if (!d) return MOT_ERR_BAD_ARG;
   if (d->abi_version != MOT_B200_ABI_VERSION) return MOT_ERR_BAD_ARG;
@@ -146,6 +160,7 @@ static int validate(const MotDesc* d) {
     if (d->col_offset < 0 || ld < (long long)d->col_offset + d->out_dim || ld > 0x7fffffffLL) return MOT_ERR_BAD_ARG;
     if (ld % 8 || d->col_offset % 8) return MOT_ERR_MISALIGNED;
   }
+  if (d->dp_slabs < 0 || d->dp_slabs > 64) return MOT_ERR_BAD_ARG;
   if ((d->flags & MOT_F_IDS_FROM_TTB) && has_bytes) {
     if (d->ttb_dtype < MOT_TTB_I16 || d->ttb_dtype > MOT_TTB_BF16) return MOT_ERR_UNSUPPORTED;
     if (d->flags & MOT_F_TTB_SCRAMBLE)
@@ -177,6 +192,9 @@ static void fill_params(const MotDesc* d, EmbedParams& p) {
   p.n_rep = kByteRep;
   p.stages = 4;
   p.tab_smem = 1;
+  p.v_lo = 0;
+  p.v_hi = p.V;
+  p.last_slab = 1;
 }
 
 // A concat without a norm over the concatenated row and without lambdas (the [tok | bytes] operand of the projection
@@ -207,11 +225,13 @@ struct WsLayout {
   size_t cnt, byte_acc, lam_acc, partial, zero_end, off, order, stok, total;
 };
 
-static WsLayout ws_layout(const EmbedParams& p) {
+static WsLayout ws_layout(const EmbedParams& p, int dp_slabs = 0) {
   WsLayout w{};
   const long long V = p.V > 0 ? p.V : 1, N = p.N > 0 ? p.N : 1;
-  // one fp32 slot per stream chunk, sized for the finer of the two chunkings (recompute / saved-output kernel)
-  const int r_min = std::min(p.R, stream_chunk(N, kSumThreads / 32));
+  // one fp32 slot per stream chunk, sized for the finest chunking in use (recompute / saved-output kernel / the slabs of
+  // the data-parallel pipeline when the descriptor announces them)
+  int r_min = std::min(p.R, stream_chunk(N, kSumThreads / 32));
+  if (dp_slabs > 1) r_min = std::min(r_min, stream_chunk_slab(N, dp_slabs, kSumThreads / 32));
   const long long n_stream_chunks = (N + r_min - 1) / r_min;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -262,7 +282,7 @@ extern "C" size_t mot_embed_workspace_bytes(const MotDesc* d) {
   if (validate(d) != MOT_OK) return 0;
   EmbedParams p;
   fill_params(d, p);
-  return ws_layout(p).total;
+  return ws_layout(p, d->dp_slabs).total;
 }
 
 extern "C" int mot_embed_fwd(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
@@ -309,7 +329,7 @@ extern "C" int mot_embed_workspace_init(const MotDesc* d, void* workspace, size_
   if (!workspace) return MOT_ERR_BAD_ARG;
   EmbedParams p;
   fill_params(d, p);
-  const WsLayout w = ws_layout(p);
+  const WsLayout w = ws_layout(p, d->dp_slabs);
   if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
   if (cudaMemsetAsync(workspace, 0, w.zero_end, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess) return check_launch();
   return MOT_OK;
@@ -322,7 +342,7 @@ extern "C" int mot_embed_plan(const MotDesc* d, const int32_t* tok, void* worksp
   if (d->combine != MOT_BYTES_ONLY && !tok) return MOT_ERR_BAD_ARG;
   EmbedParams p;
   fill_params(d, p);
-  const WsLayout w = ws_layout(p);
+  const WsLayout w = ws_layout(p, d->dp_slabs);
   if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
   if (!aligned16(workspace)) return MOT_ERR_MISALIGNED;
   bind_ws(p, w, workspace);
@@ -381,13 +401,17 @@ extern "C" int mot_embed_bwd(const MotDesc* d, const int32_t* tok, const void* b
                           g_lam, nullptr, workspace, ws_bytes, ws_flags, stream);
 }
 
-extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
-                                const void* E_tok, const void* E_byte, const float* lam, const void* addend,
-                                const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
-                                void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes,
-                                int32_t ws_flags, void* stream) {
+static int embed_bwd_impl(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                          const void* E_tok, const void* E_byte, const float* lam, const void* addend,
+                          const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
+                          void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes,
+                          int32_t ws_flags, int slab, int n_slabs, int reserve_sms, void* stream) {
   const bool plan_ready = (ws_flags & MOT_WS_PLAN_READY) != 0, ws_clean = (ws_flags & MOT_WS_CLEAN) != 0;
   if (int rc = validate(d)) return rc;
+  const bool slabbed = n_slabs > 1;
+  if (n_slabs < 1 || slab < 0 || slab >= n_slabs || reserve_sms < 0 || reserve_sms > kDpReserveMax) return MOT_ERR_BAD_ARG;
+  if (slabbed && (d->dp_slabs != n_slabs || (slab > 0 && !plan_ready))) return MOT_ERR_BAD_ARG;
+  if (slabbed && d->n_tokens == 0) return MOT_ERR_UNSUPPORTED;
   const bool has_tok = d->combine != MOT_BYTES_ONLY, has_bytes = d->combine != MOT_TOK_ONLY;
   if (has_tok && !gE_tok) return MOT_ERR_BAD_ARG;
   if (has_bytes && !gE_byte) return MOT_ERR_BAD_ARG;
@@ -416,13 +440,21 @@ extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void
     return MOT_ERR_MISALIGNED;
   EmbedParams p;
   fill_params(d, p);
-  const WsLayout w = ws_layout(p);
+  const WsLayout w = ws_layout(p, d->dp_slabs);
   if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
   bind_ws(p, w, workspace);
   p.tok = tok; p.ids = byte_ids; p.ttb = ttb; p.E_tok = E_tok; p.E_byte = E_byte; p.lam = lam;
   p.gout = grad_out; p.gE_tok = gE_tok; p.gE_byte = gE_byte; p.g_lam = g_lam;
   p.addend = addend; p.d_addend = d_addend;
+  p.plan_early = (plan_ready && (ws_flags & MOT_WS_PLAN_JOINED)) ? 1 : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (slabbed) {
+    // rows [V k / n, V (k+1) / n) of the dense token gradient; the byte table and the lambdas finish with the last slab
+    p.v_lo = (int)((long long)p.V * slab / n_slabs);
+    p.v_hi = (int)((long long)p.V * (slab + 1) / n_slabs);
+    p.last_slab = slab == n_slabs - 1;
+    p.grid_cap = 148 - reserve_sms;
+  }
   if (!plan_ready) {
     if (!ws_clean && cudaMemsetAsync(workspace, 0, w.zero_end, s) != cudaSuccess) return check_launch();
     if (int rc = run_plan(p, s)) return rc;
@@ -431,6 +463,7 @@ extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void
       return check_launch();
   }
   int rc = MOT_OK;
+  if (slabbed && concat_splits(d)) return MOT_ERR_UNSUPPORTED;
   if (concat_splits(d)) {
     EmbedParams pt, pb;
     split_params(d, pt, pb);
@@ -450,10 +483,12 @@ extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void
       p.out_saved = out_saved;
       p.rstd = rstd_saved;
       const int r_default = p.R;
-      p.R = stream_chunk(p.N, kSumThreads / 32);  // the finalize pass below reads the same p.R
+      // the finalize pass below reads the same p.R
+      p.R = slabbed ? stream_chunk_slab(p.N, n_slabs, kSumThreads / 32) : stream_chunk(p.N, kSumThreads / 32);
       rc = d->dtype == MOT_BF16 ? dispatch_bwd_sum_bf16(p, s) : dispatch_bwd_sum_f32(p, s);
       if (rc < 0) p.R = r_default;
     }
+    if (slabbed && rc < 0) return MOT_ERR_UNSUPPORTED;  // only the saved-output kernel walks a vocabulary slab
     if (rc < 0 && (addend || d_addend)) rc = d->dtype == MOT_BF16 ? dispatch_bwd_addend_bf16(p, s) : dispatch_bwd_addend_f32(p, s);
     if (rc < 0) rc = d->dtype == MOT_BF16 ? dispatch_bwd_bf16(p, s) : dispatch_bwd_f32(p, s);
   }
@@ -465,12 +500,38 @@ extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void
     long long fb = (tasks + 7) / 8;
     if (fb > 8LL * sms) fb = 8LL * sms;
     if (fb < 1) fb = 1;
+    p.trace = g_trace ? g_trace + 2 * 4096 * 64 : nullptr;
     rc = d->dtype == MOT_BF16 ? launch_finalize_bf16(p, (int)fb, s) : launch_finalize_f32(p, (int)fb, s);
   }
   if (rc) return rc;
-  if ((d->flags & MOT_F_HAS_LAMBDAS) && g_lam) {
+  if ((d->flags & MOT_F_HAS_LAMBDAS) && g_lam && p.last_slab) {
     launch_pdl(mot_lam_store_kernel, dim3(1), dim3(32), 0, s, p.lam_acc, g_lam);
     count_launch();
   }
   return check_launch();
+}
+
+extern "C" int mot_embed_bwd_ex(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                const void* E_tok, const void* E_byte, const float* lam, const void* addend,
+                                const void* grad_out, const void* out_saved, const float* rstd_saved, void* gE_tok,
+                                void* gE_byte, float* g_lam, void* d_addend, void* workspace, size_t ws_bytes,
+                                int32_t ws_flags, void* stream) {
+  return embed_bwd_impl(d, tok, byte_ids, ttb, E_tok, E_byte, lam, addend, grad_out, out_saved, rstd_saved, gE_tok, gE_byte,
+                        g_lam, d_addend, workspace, ws_bytes, ws_flags, 0, 1, 0, stream);
+}
+
+extern "C" int mot_embed_bwd_slab(const MotDesc* d, const int32_t* tok, const void* byte_ids, const void* ttb,
+                                  const void* E_tok, const void* E_byte, const float* lam, const void* grad_out,
+                                  const void* out_saved, const float* rstd_saved, void* gE_tok, void* gE_byte, float* g_lam,
+                                  void* workspace, size_t ws_bytes, int32_t ws_flags, int32_t slab, int32_t n_slabs,
+                                  int32_t reserve_sms, void* stream) {
+  return embed_bwd_impl(d, tok, byte_ids, ttb, E_tok, E_byte, lam, nullptr, grad_out, out_saved, rstd_saved, gE_tok, gE_byte,
+                        g_lam, nullptr, workspace, ws_bytes, ws_flags, slab, n_slabs, reserve_sms, stream);
+}
+
+extern "C" int mot_embed_slab_rows(int32_t tok_vocab, int32_t slab, int32_t n_slabs, int32_t* row_lo, int32_t* row_hi) {
+  if (tok_vocab <= 0 || n_slabs < 1 || slab < 0 || slab >= n_slabs || !row_lo || !row_hi) return MOT_ERR_BAD_ARG;
+  *row_lo = (int32_t)((long long)tok_vocab * slab / n_slabs);
+  *row_hi = (int32_t)((long long)tok_vocab * (slab + 1) / n_slabs);
+  return MOT_OK;
 }

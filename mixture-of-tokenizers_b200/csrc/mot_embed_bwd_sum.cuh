@@ -94,19 +94,29 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   fence_mbar_init();
   pdl_launch_dependents();
   __syncthreads();
-  pdl_wait();  // nothing above touches global memory
-
   const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs: every SM gets the same share +-1
+  MOT_STAMP(p.trace, gw, 0);
+  // The sort plan (order / stok / off) was finished before this kernel was launched when the caller joined it through an
+  // event (plan_early): the first two batches of the stream are fetched while the predecessor kernel is still draining.
+  // Everything the predecessor may have written (rstd, the saved output, the upstream gradient) waits for
+  // griddepcontrol.wait.
+  if (!p.plan_early) pdl_wait();
+
   const int W = gridDim.x * nw;
   const int Ni = (int)p.N, R = p.R;  // n_tokens < 2^31 (validated on the host): 32-bit stream math
-  const int n_stream_chunks = (Ni + R - 1) / R;
   const char* gout = reinterpret_cast<const char*>(p.gout);
   const char* osv = reinterpret_cast<const char*>(p.out_saved);
   const uint32_t row_bytes = (uint32_t)p.Do * sizeof(T);  // rows of gout / out_saved are contiguous (never a split concat)
 
-  // ---- the warp's share of the stream: chunks gw, gw + W, ... walked in batches of <= 32 entries ----
-  int nx_chunk = gw, nx_a = gw * R;  // the next batch to load
-  auto load_next = [&](SumBatch& b) {
+  // ---- this launch's part of the stream: the entries of the vocabulary rows [v_lo, v_hi), i.e. [a0, a1) (the whole
+  //      stream unless the backward runs as slabs of the data-parallel pipeline).  Chunks keep their GLOBAL numbering
+  //      (chunk c = entries [c R, (c+1) R)), clipped to [a0, a1): a slab starts and ends on a row boundary.
+  const int a0 = __ldg(p.off + p.v_lo), a1 = __ldg(p.off + p.v_hi);
+  const int c_lo = a0 / R, c_hi = (a1 + R - 1) / R;
+
+  // ---- the warp's share: chunks c_lo + gw, c_lo + gw + W, ... walked in batches of <= 32 entries ----
+  int nx_chunk = c_lo + gw, nx_a = max(nx_chunk * R, a0);  // the next batch to load
+  auto load_next = [&](SumBatch& b, bool with_r) {
     b.pos = 0;
     b.v = -1;
     b.r = 0.f;
@@ -115,15 +125,15 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
     b.flags = 0;
     b.v_prev = -1;
     b.v_next = -1;
-    if (nx_chunk >= n_stream_chunks) return;
-    const int c0 = nx_chunk * R, c_end = min(c0 + R, Ni);
+    if (nx_chunk >= c_hi) return;
+    const int c0 = max(nx_chunk * R, a0), c_end = min(nx_chunk * R + R, a1);
     const int a = nx_a, left = c_end - a;
     b.a = a;
     b.cnt = left < 32 ? left : 32;
     if (lane < b.cnt) {
       b.pos = __ldg(p.order + a + lane);
       b.v = __ldg(p.stok + a + lane);
-      b.r = __ldg(p.rstd + b.pos);
+      if (with_r) b.r = __ldg(p.rstd + b.pos);
     }
     if (a == c0) {
       b.flags |= 1;
@@ -133,14 +143,21 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
       b.flags |= 2;
       if (c_end < Ni) b.v_next = __ldg(p.stok + c_end);
       nx_chunk += W;
-      nx_a = nx_chunk < n_stream_chunks ? nx_chunk * R : 0;
+      nx_a = nx_chunk < c_hi ? max(nx_chunk * R, a0) : 0;
     } else {
       nx_a = a + 32;
     }
   };
   SumBatch A, B;
-  load_next(A);
-  load_next(B);
+  load_next(A, !p.plan_early);
+  load_next(B, !p.plan_early);
+  if (p.plan_early) {
+    pdl_wait();
+    if (lane < A.cnt) A.r = __ldg(p.rstd + A.pos);
+    if (lane < B.cnt) B.r = __ldg(p.rstd + B.pos);
+  }
+  MOT_STAMP(p.trace, gw, 1);
+  MOT_STAMP(p.trace, gw, 2);
 
   // ---- ring: occurrence n of this warp lives in stage n % D ----
   int inflight = 0;    // issued - consumed
@@ -172,6 +189,7 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   };
   while (inflight < D && try_issue()) {
   }
+  MOT_STAMP(p.trace, gw, 3);
 
   // ---- per-lane constants: byte slot and accumulator offset of each of the lane's chunks ----
   int slot[CPL];
@@ -190,26 +208,11 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   const IdSrc idsrc = make_id_src(p, lane);
   T* G = reinterpret_cast<T*>(p.gE_tok);
 
-  // ---- phase Z: rows nobody gathered get zeros (the dense-grad contract of the reference) ----
-  {
-    const float zero[CW] = {0.f, 0.f, 0.f, 0.f};
-#ifndef MOT_X_SUM_NO_ZERO
-    for (int vb = gw * 32; vb < p.V; vb += W * 32) {
-      const int v = vb + lane;
-      const bool empty = v < p.V && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
-      unsigned m = __ballot_sync(kFull, empty);
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        T* row = G + (size_t)(unsigned)(vb + j) * (unsigned)p.Dt;
-#pragma unroll
-        for (int it = 0; it < CPL; ++it) V::stg(row + (it * 32 + lane) * CW, zero);
-      }
-    }
-#endif
-  }
-
+  MOT_STAMP(p.trace, gw, 4);
   // ---- phase S: the stream ----
+#ifdef MOT_TRACE
+  int n_occ = 0;
+#endif
   float Du[CPL][CW];
 #pragma unroll
   for (int it = 0; it < CPL; ++it)
@@ -263,6 +266,10 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
       }
 
       mbar_wait_s(bars_s + (uint32_t)cs * 8u, cpar);
+#ifdef MOT_TRACE
+      MOT_STAMP(p.trace, gw, 5 + n_occ);
+      ++n_occ;
+#endif
       const T* grow = reinterpret_cast<const T*>(ring + (size_t)cs * stage_bytes);
       const T* orow = reinterpret_cast<const T*>(ring + (size_t)cs * stage_bytes + row_off);
       if (++cs == D) {
@@ -340,10 +347,48 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
     // advance: A <- B, prefetch the batch after
     A = B;
     if (iw == 1) iw = 0; else ik = 0;
-    load_next(B);
+    load_next(B, true);
     while (inflight < D && try_issue()) {  // the issue cursor may have been waiting for this batch
     }
   }
+  MOT_STAMP(p.trace, gw, 61);
+
+  // ---- phase Z (after the stream): rows nobody gathered get zeros (the dense-grad contract of the reference).  Blocks of
+  //      32 vocabulary rows are handed out by a global counter, so the warps that finish their stream first take the
+  //      zero fill (13 % of the kernel's HBM traffic at 48K tokens) while the slower ones are still streaming: the fill is
+  //      the load balancer of the kernel instead of a serial prologue in front of the first row copy.  The finalize
+  //      kernel resets the counter (self-cleaning workspace).
+#ifndef MOT_X_SUM_NO_ZERO
+  {
+    const float zero[CW] = {0.f, 0.f, 0.f, 0.f};
+    int* zctr = reinterpret_cast<int*>(p.lam_acc) + 2;
+    const int n_blocks = (p.v_hi - p.v_lo + 31) >> 5;
+    auto grab = [&]() -> int {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(zctr, 1);
+      return __shfl_sync(kFull, b, 0);
+    };
+    int nb = grab();
+    while (nb < n_blocks) {
+      const int vb = p.v_lo + (nb << 5);
+      const int v = vb + lane;
+      const bool empty = v < p.v_hi && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
+      nb = grab();  // the next block's ticket travels while this block is written
+      unsigned m = __ballot_sync(kFull, empty);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        T* row = G + (size_t)(unsigned)(vb + j) * (unsigned)p.Dt;
+#pragma unroll
+        for (int it = 0; it < CPL; ++it) V::stg(row + (it * 32 + lane) * CW, zero);
+      }
+    }
+  }
+#endif
+  MOT_STAMP(p.trace, gw, 62);
+#ifdef MOT_TRACE
+  if (p.trace != nullptr && lane == 0) p.trace[(size_t)gw * 64 + 63] = n_occ;
+#endif
 }
 
 template <typename T, int CPL>
@@ -364,10 +409,12 @@ static int launch_bwd_sum(const EmbedParams& p_in, cudaStream_t s) {
     }
   }
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
+  p.trace = g_trace ? g_trace + 4096 * 64 : nullptr;
   auto kern = mot_bwd_sum_kernel<T, CPL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   if (g_prof_start) cudaEventRecord(g_prof_start, s);
-  launch_pdl(kern, dim3((unsigned)sms), dim3(kSumThreads), smem, s, p);
+  const int ctas = (p.grid_cap > 0 && p.grid_cap < sms) ? p.grid_cap : sms;
+  launch_pdl(kern, dim3((unsigned)ctas), dim3(kSumThreads), smem, s, p);
   if (g_prof_stop) cudaEventRecord(g_prof_stop, s);
   count_launch();
   return check_launch();

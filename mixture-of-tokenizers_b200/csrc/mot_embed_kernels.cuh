@@ -61,7 +61,7 @@ struct EmbedParams {
   int* stok;        // [N]     token id of every stream entry
   float* partial;   // [n_stream_chunks, Dt] fp32 slots, zero on entry: sums of the rows that straddle chunk boundaries
   float* byte_acc;  // [n_rep, Vb*bd] fp32, zeroed per call
-  float* lam_acc;   // [2]
+  float* lam_acc;   // [2]; the int behind them (lam_acc + 2) is the zero-fill work counter of the saved-output backward
   long long N, T;
   long long io_ld;  // row stride (elements) of `out` (forward) / `gout` (backward); Do unless the call is one half of a split concat
   int io_col;       // first column of this kernel's slice inside those rows
@@ -71,7 +71,14 @@ struct EmbedParams {
   int n_rep;     // replicas of the byte-grad accumulator (spreads hot byte ids over L2 atomic units)
   int stages;    // ring depth per warp
   int tab_smem;  // 1: byte table staged in shared memory; 0: too large, rows read through L1/L2
+  int v_lo, v_hi;  // vocabulary rows [v_lo, v_hi) this launch is responsible for (a slab of the data-parallel pipeline; the
+                   // whole table: 0, V)
+  int grid_cap;    // > 0: launch at most this many CTAs (SMs left to the exchange kernel that runs beside a slab)
+  int last_slab;   // finalize: 1 = also finish the byte table and the lambdas (the last / only slab)
+  int plan_early;  // 1: the sort plan was complete before this kernel was launched (event join): its arrays may be read
+                   //    before griddepcontrol.wait
   float eps;
+  long long* trace;  // MOT_TRACE builds: per-warp time stamps (nullptr: off)
 };
 
 struct ChunkMap {
@@ -248,17 +255,21 @@ __device__ __forceinline__ typename Vec<T, CW>::Raw tab_load(const EmbedParams& 
 // never scales byte rows: the MoT-sum fast path) skips the scale pass: every thread has waited on the copy barrier
 // itself, which is all the table reads need.
 template <typename T>
-__device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar, bool need_rs) {
-  if (p.tab_smem) {
+__device__ __forceinline__ void issue_byte_table(const EmbedParams& p, T* tab, uint64_t* bar) {
+  if (p.tab_smem && threadIdx.x == 0) {
     const uint32_t bytes = (uint32_t)p.Vb * p.bd * sizeof(T);
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, bytes);
-      for (uint32_t done = 0; done < bytes;) {
-        const uint32_t n = min(bytes - done, 32768u);
-        bulk_g2s(reinterpret_cast<char*>(tab) + done, reinterpret_cast<const char*>(p.E_byte) + done, n, bar);
-        done += n;
-      }
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t done = 0; done < bytes;) {
+      const uint32_t n = min(bytes - done, 32768u);
+      bulk_g2s(reinterpret_cast<char*>(tab) + done, reinterpret_cast<const char*>(p.E_byte) + done, n, bar);
+      done += n;
     }
+  }
+}
+template <typename T>
+__device__ void stage_byte_table(const EmbedParams& p, T* tab, float* rs, uint64_t* bar, bool need_rs, bool issued = false) {
+  if (p.tab_smem) {
+    if (!issued) issue_byte_table<T>(p, tab, bar);
     mbar_wait(bar, 0);
   }
   if (!need_rs) return;
@@ -344,17 +355,21 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
   fence_mbar_init();
   pdl_launch_dependents();
   __syncthreads();
-  pdl_wait();  // nothing above touches global memory
-
   const int gw = warp * gridDim.x + blockIdx.x;  // interleaved over the CTAs: every SM gets the same share +-1
                                                  // (n_tokens < 2^31, validated on the host: 32-bit position math)
+  MOT_STAMP(p.trace, gw, 0);
+  pdl_wait();  // nothing above touches global memory
+  MOT_STAMP(p.trace, gw, 1);
+
   const int stride = gridDim.x * nw;
   const int Ni = (int)p.N;
   const int n_i = gw < Ni ? (Ni - gw + stride - 1) / stride : 0;  // positions of this warp
   const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
   const uint32_t row_bytes = (uint32_t)p.Dt * sizeof(T);
 
-  // ring prologue first (so the token rows are in flight while the byte table is staged)
+  // the byte table first (one elected thread, no dependent loads in front of it), then the ring prologue: the token rows
+  // are in flight while the table arrives
+  if (has_bytes) issue_byte_table<T>(p, tab, &tab_bar);
   int tok_ahead = 0;  // lane 0: raw token id of position i + D
   if (has_tok && lane == 0) {
     for (int i = 0; i < D && i < n_i; ++i) {
@@ -364,7 +379,9 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     }
     if (D < n_i) tok_ahead = __ldg(p.tok + gw + D * stride);  // raw; clamped where it is used
   }
-  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar, C::byte_scale(p));
+  MOT_STAMP(p.trace, gw, 2);
+  if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar, C::byte_scale(p), /*issued=*/true);
+  MOT_STAMP(p.trace, gw, 3);
 
   ChunkMap cm[CPL];
 #pragma unroll
@@ -397,6 +414,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     float ss_t = 0.f;
     if (has_tok) {
       mbar_wait(bars + s, parity);
+      MOT_STAMP(p.trace, gw, 5 + i);
       const T* trow = reinterpret_cast<const T*>(ring + (size_t)s * L.stage_bytes);
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
@@ -497,6 +515,10 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
       }
     }
   }
+  MOT_STAMP(p.trace, gw, 62);
+#ifdef MOT_TRACE
+  if (p.trace != nullptr && lane == 0) p.trace[(size_t)gw * 64 + 63] = n_i;
+#endif
 }
 
 // ======================================================================================
@@ -967,10 +989,12 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
 template <typename T>
 __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams p) {
   pdl_launch_dependents();
+  MOT_STAMP(p.trace, (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & 4095, 0);
   pdl_wait();
   const int lane = lane_id();
   const int nw = blockDim.x >> 5;
   const int gw = blockIdx.x * nw + (threadIdx.x >> 5);
+  MOT_STAMP(p.trace, gw & 4095, 1);
   const int W = gridDim.x * nw;
   const bool has_tok = p.combine != MOT_BYTES_ONLY;
   const bool has_bytes = p.combine != MOT_TOK_ONLY;
@@ -978,12 +1002,17 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
   float lam_t = 1.f;
   if (has_lam) lam_t = __ldg(p.lam);
   float dlam_t = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.lam_acc != nullptr)
+    reinterpret_cast<int*>(p.lam_acc)[2] = 0;  // zero-fill work counter of the saved-output backward (self-cleaning)
   if (has_tok) {
     const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
-    const long long n_stream_chunks = (p.N + p.R - 1) / p.R;
+    // chunk boundaries strictly inside this launch's part of the stream [off[v_lo], off[v_hi]) (the whole stream unless
+    // the backward runs as vocabulary slabs): a slab starts and ends on a row boundary, so no row crosses it
+    const long long a0 = __ldg(p.off + p.v_lo), a1 = __ldg(p.off + p.v_hi);
+    const long long c_lo = a0 / p.R, c_hi = (a1 + p.R - 1) / p.R;
     const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
     T* G = reinterpret_cast<T*>(p.gE_tok);
-    for (long long c0 = gw; c0 + 1 < n_stream_chunks; c0 += W) {
+    for (long long c0 = c_lo + gw; c0 + 1 < c_hi; c0 += W) {
       const long long bnd = (c0 + 1) * (long long)p.R;  // first stream entry of chunk c0 + 1
       const int v = __ldg(p.stok + bnd - 1);
       if (__ldg(p.stok + bnd) != v) continue;                  // no row crosses this boundary
@@ -1028,70 +1057,96 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
       }
     }
   }
-  if (has_bytes) {
-    // one warp per byte row, one lane per 8-element chunk; the kByteRep replica loads are independent (unrolled)
+  if (has_bytes && p.last_slab) {
+    // One warp per byte row.  The row has nc = bd / 8 chunks of 8 elements and kByteRep replicas: lane = group * nc + c
+    // owns chunk c of the replicas {group, group + G, ...} (G = 32 / nc lane groups), so every replica load of the row is
+    // in flight at once (one L2 round trip instead of one per 8 replicas with 6 of 32 lanes working: the byte rows were
+    // the critical path of this kernel, 5-6.6 us of 6.6, profiles/r2_timeline.md); the groups then meet through shuffles.
     const bool bn = (p.flags & MOT_F_BYTE_NORM) != 0;
     const T* E_byte = reinterpret_cast<const T*>(p.E_byte);
     T* G = reinterpret_cast<T*>(p.gE_byte);
     const size_t rep_stride = (size_t)p.Vb * p.bd;
-    const int nc = p.bd / kChunk;
-    // byte rows are the tasks after the chunk boundaries, so a grid of (boundaries + Vb) warps gives one task per warp
-    const int nb_ = has_tok ? (int)((p.N + p.R - 1) / p.R) - 1 : 0;
-    for (int t_ = gw; t_ < nb_ + p.Vb; t_ += W) {
-      const int r = t_ - nb_;
-      if (r < 0) continue;
-      for (int c0 = 0; c0 < nc; c0 += 32) {  // bd <= 256 for every reference config: one trip
-        const int c = c0 + lane;
-        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (c < nc) {
-          const float* src = p.byte_acc + (size_t)r * p.bd + c * kChunk;
-          // groups of 8 replicas: 16 independent 16-byte loads in flight, zeroed again for the next call (the
-          // workspace cleans itself, see MOT_WS_CLEAN), then summed
-          float* dst = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+    const int nc = p.bd / kChunk;  // <= 32 (bd <= 256, validated on the host for byte_norm; wider rows take the slow loop)
+    // byte rows are handed out from the LAST warp of the grid backwards (the chunk boundaries above from the first
+    // forwards), so a grid of (boundaries + Vb) warps gives one task per warp
+    for (int r = W - 1 - gw; r < p.Vb; r += W) {
+      if (nc <= 32) {
+        const int ngrp = 32 / nc;                    // lane groups (>= 1)
+        const int grp = lane / nc, c = lane - grp * nc;
+        const bool live = grp < ngrp;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+          float* base = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+          // replicas grp, grp + G, grp + 2G, ...: four per trip (bd <= 64: one trip covers all 16)
 #pragma unroll 1
-          for (int r0 = 0; r0 < kByteRep; r0 += 8) {
-            float4 x[8], y[8];
+          for (int j0 = 0; grp + j0 * ngrp < kByteRep; j0 += 4) {
+            float4 x[4], y[4];
 #pragma unroll
-            for (int rep = 0; rep < 8; ++rep) {
-              if (r0 + rep < kByteRep) {
-                x[rep] = *reinterpret_cast<const float4*>(src + (r0 + rep) * rep_stride);
-                y[rep] = *reinterpret_cast<const float4*>(src + (r0 + rep) * rep_stride + 4);
+            for (int j = 0; j < 4; ++j) {
+              const int rep = grp + (j0 + j) * ngrp;
+              if (rep < kByteRep) {
+                x[j] = *reinterpret_cast<const float4*>(base + rep * rep_stride);
+                y[j] = *reinterpret_cast<const float4*>(base + rep * rep_stride + 4);
               }
             }
 #pragma unroll
-            for (int rep = 0; rep < 8; ++rep) {
-              if (r0 + rep < kByteRep) {
-                *reinterpret_cast<float4*>(dst + (r0 + rep) * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(dst + (r0 + rep) * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-#pragma unroll
-            for (int rep = 0; rep < 8; ++rep) {
-              if (r0 + rep < kByteRep) {
-                a[0] += x[rep].x; a[1] += x[rep].y; a[2] += x[rep].z; a[3] += x[rep].w;
-                a[4] += y[rep].x; a[5] += y[rep].y; a[6] += y[rep].z; a[7] += y[rep].w;
+            for (int j = 0; j < 4; ++j) {
+              const int rep = grp + (j0 + j) * ngrp;
+              if (rep < kByteRep) {  // zeroed again for the next call (the workspace cleans itself, MOT_WS_CLEAN)
+                *reinterpret_cast<float4*>(base + rep * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(base + rep * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                a[0] += x[j].x; a[1] += x[j].y; a[2] += x[j].z; a[3] += x[j].w;
+                a[4] += y[j].x; a[5] += y[j].y; a[6] += y[j].z; a[7] += y[j].w;
               }
             }
           }
-          if (bn) Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
         }
-        float rsr = 1.f, b_ = 0.f;
-        if (bn) {  // rows wider than 256 elements would need a cross-trip reduction; refused on the host
-          float dot = 0.f, ss = 0.f;
+        // group g adds into group 0: lane c receives from lanes c + g * nc (fixed order: deterministic given the replicas)
+        for (int g2 = 1; g2 < ngrp; ++g2) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            dot += a[e] * ev[e];
-            ss += ev[e] * ev[e];
+            const float o_ = __shfl_sync(0xffffffffu, a[e], (lane + g2 * nc) & 31);
+            if (lane < nc) a[e] += o_;
+          }
+        }
+        float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool owner = lane < nc;
+        if (bn && owner) Vec8<T>::unpack(Vec8<T>::ldg_raw(E_byte + (size_t)r * p.bd + c * kChunk), ev);
+        float rsr = 1.f, b_ = 0.f;
+        if (bn) {
+          float dot = 0.f, ss = 0.f;
+          if (owner) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              dot += a[e] * ev[e];
+              ss += ev[e] * ev[e];
+            }
           }
           warp_sum2(dot, ss);
           rsr = rsqrtf(ss / (float)p.bd + p.eps);
           b_ = rsr * rsr * rsr * dot / (float)p.bd;
         }
-        if (c < nc) {
+        if (owner) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = rsr * a[e] - b_ * ev[e];
           Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, o);
+        }
+      } else {
+        // rows wider than 256 elements (no byte norm: refused on the host): one lane per chunk, replicas in turn
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int c = c0 + lane;
+          if (c >= nc) continue;
+          float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float* base = p.byte_acc + (size_t)r * p.bd + c * kChunk;
+          for (int rep = 0; rep < kByteRep; ++rep) {
+            const float4 x = *reinterpret_cast<const float4*>(base + rep * rep_stride);
+            const float4 y = *reinterpret_cast<const float4*>(base + rep * rep_stride + 4);
+            *reinterpret_cast<float4*>(base + rep * rep_stride) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(base + rep * rep_stride + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w; a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
+          }
+          Vec8<T>::stg(G + (size_t)r * p.bd + c * kChunk, a);
         }
       }
     }
@@ -1100,6 +1155,7 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
     dlam_t = warp_sum(dlam_t);
     if (lane == 0 && dlam_t != 0.f) atomicAdd(p.lam_acc, dlam_t);
   }
+  MOT_STAMP(p.trace, gw & 4095, 62);
 }
 
 // ======================================================================================
@@ -1139,6 +1195,7 @@ static int launch_fwd(const EmbedParams& p_in, cudaStream_t s) {
   }
   if (smem == 0) return MOT_ERR_UNSUPPORTED;
   if ((MODE == 1 || MOT_ADDFAM(MODE)) && !p.tab_smem) return launch_fwd<T, CPL, 0>(p_in, s);  // fast paths assume the table in smem
+  p.trace = g_trace;
   auto kern = mot_fwd_kernel<T, CPL, MODE, NT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
   const long long warps_needed = p.N;

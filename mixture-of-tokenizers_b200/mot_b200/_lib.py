@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmot_b200" + os.environ.get("MOT_LIB_SUFFIX", "") + ".so")  # suffix: experiment builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 # enums of include/mot_b200.h
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_MISALIGNED, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = range(7)
 BF16, F32 = 0, 1
@@ -21,7 +21,7 @@ TTB_I16, TTB_F32, TTB_BF16 = 0, 1, 2
 ADD, CONCAT, TOK_ONLY, BYTES_ONLY, MEAN = range(5)
 F_TOK_NORM, F_BYTE_NORM, F_OUT_NORM, F_BYTES_FIRST = 1, 2, 4, 8
 F_SLOT_MAJOR, F_IDS_FROM_TTB, F_TTB_SCRAMBLE, F_IDS_I64, F_HAS_LAMBDAS = 16, 32, 64, 128, 256
-WS_PLAN_READY, WS_CLEAN = 1, 2
+WS_PLAN_READY, WS_CLEAN, WS_PLAN_JOINED = 1, 2, 4
 
 
 class MotDesc(C.Structure):
@@ -32,7 +32,7 @@ class MotDesc(C.Structure):
         ("tok_dim", C.c_int32), ("byte_dim", C.c_int32), ("out_dim", C.c_int32),
         ("combine", C.c_int32), ("flags", C.c_int32), ("ttb_dtype", C.c_int32),
         ("eps", C.c_float),
-        ("row_stride", C.c_int64), ("col_offset", C.c_int32), ("reserved", C.c_int32),
+        ("row_stride", C.c_int64), ("col_offset", C.c_int32), ("dp_slabs", C.c_int32),
     ]
 
 
@@ -44,6 +44,7 @@ _SIGNATURES = {
     "mot_launch_count": (C.c_int64, []),
     "mot_launch_count_reset": (None, []),
     "mot_profile_events": (None, [_P, _P, _P, _P]),
+    "mot_profile_trace": (None, [_P]),
     "mot_ttb_expand": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
     "mot_ttb_build": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mot_ttb_repad": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
@@ -59,6 +60,9 @@ _SIGNATURES = {
     "mot_embed_fwd_ex": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mot_embed_bwd_ex": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    C.c_size_t, C.c_int32, _P]),
+    "mot_embed_bwd_slab": (C.c_int, [C.POINTER(MotDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "mot_embed_slab_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mot_tokens_widen_u16": (C.c_int, [_P, C.c_int64, _P, _P]),
     "mot_embed_bwd_uses_saved": (C.c_int, [C.POINTER(MotDesc)]),
     "mot_byte_pair_fwd": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P,

@@ -161,7 +161,7 @@ def embed_bwd_op(grad_out: Tensor, tok: Optional[Tensor], ids: Optional[Tensor],
     O.embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok if E_tok is not None else None,
                          gE_byte if E_byte is not None else None, g_lam if lam is not None else None, ws,
                          plan_ready=planned, ws_clean=planned, out_saved=out_saved if keep else None,
-                         rstd=rstd if keep else None)
+                         rstd=rstd if keep else None, plan_joined=planned)
     return gE_tok, gE_byte, g_lam
 
 

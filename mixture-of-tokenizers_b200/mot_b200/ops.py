@@ -177,7 +177,7 @@ def pull_from_right(byte_tensor: torch.Tensor, bytes_per_token: int, pad_byte: i
 
 def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Optional[torch.Tensor],
               ttb: Optional[torch.Tensor], has_lam: bool, seq_len: int = 0, row_stride: int = 0,
-              col_offset: int = 0) -> L.MotDesc:
+              col_offset: int = 0, dp_slabs: int = 0) -> L.MotDesc:
     ref = E_tok if E_tok is not None else E_byte
     if ref.dtype not in _DTYPE:
         raise NotImplementedError(f"mot_b200: embedding dtype {ref.dtype} is not supported (bf16 / fp32 only)")
@@ -211,7 +211,7 @@ def make_desc(spec: MixSpec, n_tokens: int, E_tok, E_byte, bpt: int, *, ids: Opt
             flags |= L.F_IDS_I64 if ids.dtype == torch.int64 else 0
     return L.MotDesc(L.ABI_VERSION, _DTYPE[ref.dtype], n_tokens, seq_len,
                      E_tok.shape[0] if has_tok else 0, E_byte.shape[0] if has_bytes else 0, bpt if has_bytes else 0,
-                     Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps, row_stride, col_offset, 0)
+                     Dt, bd, Do, _COMBINE[spec.combine], flags, ttb_dtype, spec.eps, row_stride, col_offset, dp_slabs)
 
 
 def embed_forward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, out, stream: Optional[int] = None,
@@ -257,12 +257,15 @@ def embed_plan(desc: L.MotDesc, tok, ws, ws_clean: bool = False) -> None:
 def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, gE_tok, gE_byte, g_lam, ws,
                        plan_ready: bool = False, ws_clean: bool = False, stream: Optional[int] = None,
                        out_saved: Optional[torch.Tensor] = None, rstd: Optional[torch.Tensor] = None,
-                       addend: Optional[torch.Tensor] = None, d_addend: Optional[torch.Tensor] = None) -> None:
+                       addend: Optional[torch.Tensor] = None, d_addend: Optional[torch.Tensor] = None,
+                       plan_joined: bool = False) -> None:
     """mot_embed_bwd on caller-allocated tensors; gE_tok / gE_byte are fully overwritten.  `ws_clean`: the caller
     vouches that the head of `ws` is zero (fresh from embed_workspace_init or left by a completed backward).
+    `plan_joined`: the plan ran on the side stream and this stream waited for its event (MOT_WS_PLAN_JOINED).
     `out_saved` + `rstd` (what embed_forward_out(..., rstd=) produced) and `addend` / `d_addend`: mot_embed_bwd_ex."""
     dev = grad_out.device
-    flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0)
+    flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0) | \
+        (L.WS_PLAN_JOINED if plan_ready and plan_joined else 0)
     with _on_device(dev):
         if (out_saved is None or rstd is None) and addend is None and d_addend is None:
             rc = L.lib().mot_embed_bwd(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
@@ -274,6 +277,30 @@ def embed_backward_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_
                                           _ptr(gE_byte), _ptr(g_lam), _ptr(d_addend), _ptr(ws), ws.numel(), flags,
                                           _stream(dev) if stream is None else stream)
     L.check(rc, "mot_embed_bwd")
+
+
+def embed_backward_slab_out(desc: L.MotDesc, tok, ids, ttb, E_tok, E_byte, lam, grad_out, out_saved, rstd, gE_tok, gE_byte,
+                            g_lam, ws, slab: int, n_slabs: int, *, reserve_sms: int = 0, plan_ready: bool = True,
+                            ws_clean: bool = True, plan_joined: bool = False, stream: Optional[int] = None) -> None:
+    """mot_embed_bwd_slab: slab `slab` of `n_slabs` of the backward (rows slab_rows(...) of gE_tok are final once its
+    kernels have run; gE_byte / g_lam after the last slab).  desc must have been made with dp_slabs=n_slabs."""
+    dev = grad_out.device
+    flags = (L.WS_PLAN_READY if plan_ready else 0) | (L.WS_CLEAN if ws_clean else 0) | \
+        (L.WS_PLAN_JOINED if plan_ready and plan_joined else 0)
+    with _on_device(dev):
+        rc = L.lib().mot_embed_bwd_slab(desc, _ptr(tok), _ptr(ids), _ptr(ttb), _ptr(E_tok), _ptr(E_byte), _ptr(lam),
+                                        _ptr(grad_out), _ptr(out_saved), _ptr(rstd), _ptr(gE_tok), _ptr(gE_byte), _ptr(g_lam),
+                                        _ptr(ws), ws.numel(), flags, slab, n_slabs, reserve_sms,
+                                        _stream(dev) if stream is None else stream)
+    L.check(rc, "mot_embed_bwd_slab")
+
+
+def slab_rows(tok_vocab: int, slab: int, n_slabs: int):
+    """Rows [lo, hi) of the token table that slab `slab` of `n_slabs` owns (mot_embed_slab_rows)."""
+    import ctypes as C
+    lo, hi = C.c_int32(), C.c_int32()
+    L.check(L.lib().mot_embed_slab_rows(tok_vocab, slab, n_slabs, C.byref(lo), C.byref(hi)), "mot_embed_slab_rows")
+    return lo.value, hi.value
 
 
 class Workspace:
@@ -313,7 +340,7 @@ _SIDE_STREAMS: dict = {}
 def acquire_workspace(desc: L.MotDesc, dev) -> Workspace:
     # the zeroed head of the workspace (histogram | byte accumulators | one fp32 slot per stream chunk) is laid out by the
     # table geometry AND by (n_tokens, tok_dim): a buffer is only "clean" for the exact layout it was last used with
-    key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine, desc.n_tokens, desc.tok_dim)
+    key = (dev.index, desc.tok_vocab, desc.byte_vocab, desc.byte_dim, desc.combine, desc.n_tokens, desc.tok_dim, desc.dp_slabs)
     free = _WS_POOL.get(key)
     if free is None:
         free = _WS_POOL[key] = []
@@ -443,7 +470,7 @@ class _MotEmbedFn(torch.autograd.Function):
         else:
             clean, ws.clean = ws.clean, False
         embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
-                           plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd)
+                           plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd, plan_joined=planned)
         ws.clean = True           # every completed backward leaves the head of the workspace zeroed
         ctx.ws = None
         release_workspace(ws)
