@@ -308,21 +308,41 @@ def run_ours(args):
     desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N)
     if ops.embed_bwd_uses_saved(desc):
         rstd = torch.empty(N, dtype=torch.float32, device=dev)
+    # N > 1: where the bucket lives in symmetric memory and the variant has the saved-output backward, the step is a
+    # PIPELINE: the backward walks the vocabulary in slabs and the rows of slab k are averaged across ranks on the
+    # exchange stream while slab k + 1 is computed (mot_embed_bwd_slab + mot_dp_exchange); else one exchange after it.
+    n_slabs = bucket.n_slabs if (world > 1 and bucket.pipelined and rstd is not None and not os.environ.get("MOT_DP_NO_OVERLAP")) else 1
+    if n_slabs > 1:
+        desc = ops.make_desc(spec, N, E_tok, E_byte, bpt, ids=ids, ttb=None, has_lam=lam is not None, seq_len=N, dp_slabs=n_slabs)
     ws = ops.acquire_workspace(desc, dev)   # kept across steps: every completed backward leaves it clean (no memset)
     main_stream = torch.cuda.current_stream(dev)
 
-    def step():
+    def compute_step(exchange=True):
         # the same call sequence as mot_b200.mot_embed + autograd: the backward plan (counting sort of the token ids)
         # is launched on a side stream beside the forward kernel, the backward waits for it
         ops.embed_plan_async(desc, tok, ws, dev)
         ops.embed_forward_out(desc, tok, ids, None, E_tok, E_byte, lam, out, rstd=rstd)
         ops.embed_plan_join(ws, dev)
+        if n_slabs > 1:
+            for k in range(n_slabs):
+                ops.embed_backward_slab_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, out, rstd, gE_tok, gE_byte, g_lam,
+                                            ws.buf, k, n_slabs, reserve_sms=bucket.reserve_sms if k > 0 else 0, plan_joined=True)
+                if exchange:
+                    lo, hi = ops.slab_rows(V_TOK, k, n_slabs)
+                    bucket.exchange_async(lo * Dt, hi * Dt if k < n_slabs - 1 else bucket.flat.numel(), last=(k == n_slabs - 1))
+            ws.clean = True
+            if exchange:
+                bucket.wait()
+            return
         ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, lam, gout, gE_tok, gE_byte, g_lam, ws.buf,
                                plan_ready=True, ws_clean=True, out_saved=out if rstd is not None else None, rstd=rstd,
                                plan_joined=True)
         ws.clean = True
-        if world > 1:
+        if world > 1 and exchange:
             bucket.all_reduce_avg()
+
+    def step():
+        compute_step(True)
 
     def barrier():
         if world > 1:
@@ -372,6 +392,47 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / K
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / K
+
+    # ---- N > 1: the exchange alone, the compute alone, and a value check of the exchanged bucket ----
+    dp_info = None
+    if world > 1:
+        def timed(fn, reps):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            barrier()
+            t_ = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+        ar_ms = timed(bucket.all_reduce_avg, max(10, K // 4))                 # the whole bucket, one exchange
+        comp_ms = timed(lambda: compute_step(False), max(10, K // 4))         # fwd + bwd (slabs), no exchange
+        nccl_buf = bucket.flat.clone()
+        nccl_ms = timed(lambda: dist.all_reduce(nccl_buf, op=dist.ReduceOp.AVG), max(10, K // 4))
+        # value check: one more step, then rank-local gradients averaged in fp32 by NCCL
+        compute_step(False)
+        torch.cuda.synchronize()
+        want = bucket.flat.float()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        want /= world
+        step()
+        torch.cuda.synchronize()
+        err = float((bucket.flat.float() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+        errt = torch.tensor([err], device=dev)
+        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+        dp_info = {"exchange": bucket.algo, "n_slabs": n_slabs, "reserve_sms": bucket.reserve_sms if n_slabs > 1 else 0,
+                   "allreduce_ms": ar_ms, "nccl_allreduce_ms": nccl_ms, "compute_only_ms": comp_ms,
+                   "bucket_mb": bucket.flat.numel() * esz / 1e6,
+                   "allreduce_algbw_gbs": bucket.flat.numel() * esz / (ar_ms * 1e-3) / 1e9,
+                   "exposed_exchange_ms": ms_step - comp_ms,
+                   "kernel_only_tokens_per_sec": world * N / (comp_ms * 1e-3),
+                   "bucket_max_rel_err_vs_fp32_nccl": float(errt.item()), "bucket_check": "ok" if float(errt.item()) <= 2.0 ** -7 else "FAILED"}
+        if dp_info["bucket_check"] != "ok":
+            print(f"bench: exchanged bucket differs from the fp32 NCCL reference by {float(errt.item()):.3e}", file=sys.stderr)
 
     # ---- e2e: module API, ids in pinned host memory, H2D every step, D2H of the byte-table gradient ----
     e2e = None
@@ -491,8 +552,8 @@ def run_ours(args):
                        "byte_dim": bd, "bytes_per_token": bpt, "out_dim": Do, "token_dist": args.dist,
                        "byte_ids": "uniform randint(0,458), given as a tensor (runs/7:635 layout)",
                        "l2": f"working set {(2 * V_TOK * Dt * esz + 2 * N * Do * esz) / 1e6:.0f} MB > 126 MB L2, no flush",
-                       "parallelism": f"dp{world}" + ((", one flat-bucket all-reduce(AVG) per step: " +
-                                                       ("own NVLS kernel over multicast symmetric memory" if bucket._symm is not None else "NCCL"))
+                       "parallelism": f"dp{world}" + ((f", flat gradient bucket averaged per step by {bucket.algo}" +
+                                                       (f" in {n_slabs} vocabulary slabs beside the backward" if n_slabs > 1 else " after the backward"))
                                                       if world > 1 else "")},
             "tokens_per_sec_per_gpu": value / world,
             "kernel_ms": {"fwd": fwd_ms, "bwd_main": bwd_ms},
@@ -509,6 +570,8 @@ def run_ours(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if dp_info is not None:
+            line["dp"] = dp_info
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu_reference(w, steps=50, warmup=2, budget_s=15.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -707,6 +770,8 @@ def run_proj(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if dp_info is not None:
+            line["dp"] = dp_info
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu_reference(w, steps=20, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -254,12 +254,27 @@ int mot_byte_pair_bwd(const void* ids_a, const void* ids_b, int32_t ids_i64, int
                       const void* grad_out, int64_t row_stride, int32_t col_offset, void* gE_byte, void* workspace,
                       size_t ws_bytes, void* stream);
 
-/* ---- data-parallel exchange: average the gradient bucket across ranks through NVLink / NVSwitch (NVLS) -----------
- * Replaces the per-parameter dist.all_reduce(param.grad, AVG) of spt/train_gpt.py:1320-1321 and runs/7:697-700 for the
- * tensors this path owns.  `multicast_ptr` is the multicast mapping of the same symmetric-memory buffer on every rank
- * (n_bytes, multiple of 16); `signal_pads_dev` a device array of `world` pointers to the ranks' zero-initialised
- * uint32 signal pads (>= 128*world slots); `epoch` a call counter that grows by one per call on every rank (start at
- * 1).  In place, result on every rank; ordered on `stream` after the local backward. */
+/* ---- data-parallel exchange: average the gradient bucket across ranks through NVLink / NVSwitch -----------------
+ * Replaces the per-parameter dist.all_reduce(param.grad, AVG) of spt/train_gpt.py:1320-1321 and runs/7:697-700 (launched
+ * asynchronously and waited per optimizer in the runs, :697-711) for the tensors this path owns.
+ * The bucket is one symmetric-memory buffer per rank (same size everywhere):
+ *   multicast_ptr    : this rank's multicast mapping of all copies (NVLS), or NULL
+ *   peer_ptrs_dev    : device array of `world` pointers, entry q = rank q's copy as addressable from this rank (P2P), or NULL
+ *   signal_pads_dev  : device array of `world` pointers to the ranks' zero-initialised uint32 signal pads (>= 9216 bytes)
+ * mot_dp_exchange averages the byte range [byte_offset, byte_offset + n_bytes) of the bucket in place on every rank
+ * (both multiples of 16).  Every rank makes the same sequence of calls.  `epoch` is the caller's barrier counter: the
+ * call uses `epoch` for its entry barrier and, when `last` != 0, `epoch + 1` for an exit barrier -- so it grows by 1
+ * per call and by 2 after a `last` call (start at 1).  A step that exchanges its bucket in several ranges (one per
+ * mot_embed_bwd_slab) sets `last` on the final one only: ranges of one step are disjoint, and the exit barrier is what
+ * lets every rank reuse the bucket afterwards.  Ordered on `stream` after the local backward of the range.
+ *   algo MOT_DP_NVLS : multimem.ld_reduce / multimem.st through the multicast mapping (reduction inside the switch)
+ *        MOT_DP_P2P  : loads / stores through the peer pointers, fp32 accumulation in rank order (world 2, 4 or 8) */
+enum { MOT_DP_NVLS = 0, MOT_DP_P2P = 1 };
+int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, int32_t rank,
+                    int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch, int32_t last,
+                    int32_t algo, void* stream);
+/* The whole bucket as one NVLS range with both barriers (= mot_dp_exchange(..., 0, n_bytes, ..., last = 1, MOT_DP_NVLS)):
+ * `epoch` grows by 2 per call. */
 int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
                          int32_t dtype, uint32_t epoch, void* stream);
 

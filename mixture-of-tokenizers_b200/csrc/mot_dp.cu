@@ -1,24 +1,33 @@
 // The one exchange step of the path: average the dense gradients of the replicated tables across the data-parallel
-// ranks (reference: one dist.all_reduce(param.grad, AVG) per parameter, spt/train_gpt.py:1320-1321, runs/7:697-700).
+// ranks (reference: one dist.all_reduce(param.grad, AVG) per parameter, spt/train_gpt.py:1320-1321, runs/7:697-700;
+// the runs launch them asynchronously and wait per optimizer, runs/7:697-711).
 //
-// The flat gradient bucket the backward kernels wrote lives in symmetric memory that is also mapped as ONE multicast
-// address range over all ranks' copies (NVLink 5 / NVSwitch, NVLS).  One kernel per rank, two-shot through the switch:
-//   barrier (signal pads, release/acquire at system scope): every rank's backward has finished writing its copy
-//   rank r owns slice r of the bucket: multimem.ld_reduce pulls that slice from ALL copies, summed inside the switch
-//     with fp32 accumulation; scale by 1/world; multimem.st pushes the averaged slice back to ALL copies
-//   barrier: every slice has landed everywhere before any rank reads the bucket
-// Per GPU and direction about one bucket size crosses NVLink, independent of the number of ranks.
+// The flat gradient bucket the backward kernels write lives in symmetric memory: every rank can address every rank's
+// copy (peer pointers over NVLink 5 / NVSwitch) and, where the switch offers it, all copies through ONE multicast
+// address (NVLS).  The exchange works on byte RANGES of the bucket so that it can run slab by slab beside the
+// backward (mot_embed_bwd_slab): range k is exchanged on a second stream while the backward of slab k + 1 runs.
+//
+// One kernel per rank and range, two-shot: rank r owns sub-slice r of the range,
+//   barrier   (signal pads, release / acquire at system scope): every rank's backward has written the range
+//   NVLS    : multimem.ld_reduce pulls the sub-slice from ALL copies, summed inside the switch with fp32 accumulation;
+//             scale by 1 / world; multimem.st pushes the averaged values back to ALL copies.  Per GPU and direction
+//             about (1 + 1/world) range sizes cross NVLink, independent of the number of ranks.
+//   P2P     : the sub-slice is read from every rank's copy through the peer pointers (rank order: one fixed fp32
+//             summation order, the same value everywhere), averaged, and written to every copy.  2 (world-1)/world
+//             range sizes per direction: less than NVLS's (1 + 1/world) at 2 ranks, the same at ... never again, so
+//             the library picks P2P at 2 ranks, NVLS from 4 on (measured: profiles/r2_dp.md).
+//   barrier   only after the LAST range of a step: the ranges of one step touch disjoint addresses, and a rank's next
+//             step cannot write the bucket before its own last exchange kernel has passed that barrier.
 #include <cstdlib>
 
 #include "mot_common.cuh"
 
 namespace mot {
 
-// Few, fat CTAs: the switch round trip is microseconds and the links saturate with about 1 MB in flight per rank; more
-// CTAs only add contention inside the switch (8 ranks, 77 MB bf16: 8 x 1024 threads 195 us, 16 x 1024 203 us, 36 x 1024
-// 219 us, 144 x 512 239 us, NCCL 270 us; profiles/r1_experiments.md).
 constexpr int kArThreads = 1024;
-constexpr int kArMaxBlocks = 8;     // signal-pad slots used: blocks x world uint32 (torch's pad is 9216 B = 2304 slots)
+constexpr int kArMaxBlocksNvls = 8;   // measured best for the in-switch reduction (8 ranks: 8 CTAs 195 us, 36 CTAs 219 us)
+constexpr int kArMaxBlocksP2p = 32;   // 512-thread CTAs (up to 64 data registers per thread in flight)
+constexpr int kPadSlots = 9216 / 4;   // torch's signal pad: 9216 bytes of uint32 slots
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -29,7 +38,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 // Block b of every rank meets block b of every other rank: lane r tells rank r "rank `rank` reached `target`", then
-// waits until rank r said the same.  Counters only grow, so nothing is ever reset.
+// waits until rank r said the same.  The slots only grow (signed-difference compare: wrap safe), so nothing is ever
+// reset, and a block that did not take part in an earlier, smaller launch simply jumps to the current target.
 __device__ __forceinline__ void rank_barrier(uint32_t* const* pads, int rank, int world, uint32_t target) {
   __syncthreads();
   if ((int)threadIdx.x < world) {
@@ -42,14 +52,28 @@ __device__ __forceinline__ void rank_barrier(uint32_t* const* pads, int rank, in
   __syncthreads();
 }
 
+__device__ __forceinline__ void scale_vec(uint32_t (&r)[4], float inv, bool bf16) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (bf16) {
+      float lo_f, hi_f;
+      bf16x2_to_f32(r[j], lo_f, hi_f);
+      r[j] = f32x2_to_bf16x2(lo_f * inv, hi_f * inv);
+    } else {
+      r[j] = __float_as_uint(__uint_as_float(r[j]) * inv);
+    }
+  }
+}
+
 template <bool BF16, int kUnroll>
-__global__ void __launch_bounds__(1024) nvls_allreduce_avg_kernel(char* mc, uint32_t* const* pads, int rank, int world,
-                                                                        long long n_vec /* 16-byte vectors */, uint32_t epoch) {
+__global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_kernel(char* mc, uint32_t* const* pads, int rank, int world,
+                                                                        long long vec_lo, long long n_vec /* 16-byte vectors */,
+                                                                        uint32_t epoch, int last) {
   pdl_launch_dependents();
-  pdl_wait();  // the local backward / finalize kernels have completed: this rank's copy is final
-  rank_barrier(pads, rank, world, 2u * epoch + 1u);
+  pdl_wait();  // the local backward / finalize kernels of this range have completed: this rank's copy is final
+  rank_barrier(pads, rank, world, epoch);
   const long long per = (n_vec + world - 1) / world;
-  const long long lo = per * rank, hi = min(lo + per, n_vec);
+  const long long lo = vec_lo + per * rank, hi = min(lo + per, vec_lo + n_vec);
   const float inv = 1.f / (float)world;
   // kUnroll independent 16-byte reductions in flight per thread: one switch round trip is microseconds, the link wants
   // megabytes outstanding
@@ -73,62 +97,158 @@ __global__ void __launch_bounds__(1024) nvls_allreduce_avg_kernel(char* mc, uint
     for (int u = 0; u < kUnroll; ++u) {
       const long long i = i0 + u * stride;
       if (i < hi) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (BF16) {
-            float lo_f, hi_f;
-            bf16x2_to_f32(r[u][j], lo_f, hi_f);
-            r[u][j] = f32x2_to_bf16x2(lo_f * inv, hi_f * inv);
-          } else {
-            r[u][j] = __float_as_uint(__uint_as_float(r[u][j]) * inv);
-          }
-        }
+        scale_vec(r[u], inv, BF16);
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 16), "r"(r[u][0]), "r"(r[u][1]),
                      "r"(r[u][2]), "r"(r[u][3])
                      : "memory");
       }
     }
   }
-  rank_barrier(pads, rank, world, 2u * epoch + 2u);
+  if (last) rank_barrier(pads, rank, world, epoch + 1u);
+}
+
+__device__ __forceinline__ void ld_sys_16(const char* p, uint32_t (&r)[4]) {
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_sys_16(char* p, const uint32_t (&r)[4]) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+// Peer-to-peer two-shot: WORLD copies are read and written through the peer pointers.  kUnroll x WORLD 16-byte loads in
+// flight per thread (an NVLink round trip is about 2 us: a rank needs megabytes outstanding to fill 900 GB/s).
+template <bool BF16, int WORLD, int kUnroll>
+__global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* peers, uint32_t* const* pads, int rank,
+                                                                       long long vec_lo, long long n_vec, uint32_t epoch, int last) {
+  pdl_launch_dependents();
+  pdl_wait();
+  rank_barrier(pads, rank, WORLD, epoch);
+  char* P[WORLD];
+#pragma unroll
+  for (int q = 0; q < WORLD; ++q) P[q] = peers[q];
+  const long long per = (n_vec + WORLD - 1) / WORLD;
+  const long long lo = vec_lo + per * rank, hi = min(lo + per, vec_lo + n_vec);
+  const float inv = 1.f / (float)WORLD;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
+    uint32_t v[kUnroll][WORLD][4];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + i * 16, v[u][q]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (BF16) {  // fp32 accumulation in rank order 0 .. WORLD-1: the same value on every rank, run to run
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) {
+              float lo_f, hi_f;
+              bf16x2_to_f32(v[u][q][j], lo_f, hi_f);
+              a += lo_f;
+              b += hi_f;
+            }
+            r[j] = f32x2_to_bf16x2(a * inv, b * inv);
+          } else {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) a += __uint_as_float(v[u][q][j]);
+            r[j] = __float_as_uint(a * inv);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + i * 16, r);
+      }
+    }
+  }
+  if (last) rank_barrier(pads, rank, WORLD, epoch + 1u);
+}
+
+template <bool BF16, int WORLD>
+static void launch_p2p(int unroll, dim3 g, dim3 b, cudaStream_t s, char* const* peers, uint32_t* const* pads, int rank,
+                       long long vec_lo, long long n_vec, uint32_t epoch, int last) {
+  if (unroll >= 4 && WORLD <= 4)
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 4>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
+  else if (unroll >= 2 && WORLD <= 8)
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 2>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
+  else
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
 }
 
 }  // namespace mot
 
 using namespace mot;
 
-extern "C" int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
-                                    int32_t dtype, uint32_t epoch, void* stream) {
-  if (!multicast_ptr || !signal_pads_dev || world < 1 || rank < 0 || rank >= world || n_bytes < 0) return MOT_ERR_BAD_ARG;
+extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, int32_t rank,
+                               int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch, int32_t last,
+                               int32_t algo, void* stream) {
+  if (!signal_pads_dev || world < 1 || rank < 0 || rank >= world || n_bytes < 0 || byte_offset < 0) return MOT_ERR_BAD_ARG;
   if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(multicast_ptr) & 15u) || (n_bytes & 15)) return MOT_ERR_MISALIGNED;
+  if (algo == MOT_DP_NVLS && !multicast_ptr) return MOT_ERR_BAD_ARG;
+  if (algo == MOT_DP_P2P && !peer_ptrs_dev) return MOT_ERR_BAD_ARG;
+  if (algo != MOT_DP_NVLS && algo != MOT_DP_P2P) return MOT_ERR_UNSUPPORTED;
+  if (algo == MOT_DP_P2P && world != 2 && world != 4 && world != 8) return MOT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(multicast_ptr) & 15u) || (n_bytes & 15) || (byte_offset & 15)) return MOT_ERR_MISALIGNED;
   if (world > 16) return MOT_ERR_UNSUPPORTED;
-  if (n_bytes == 0) return MOT_OK;
+  if (n_bytes == 0 && !last) return MOT_OK;
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
-  const long long n_vec = n_bytes / 16;
+  const long long n_vec = n_bytes / 16, vec_lo = byte_offset / 16;
   const char* env_b = getenv("MOT_AR_BLOCKS");    // debug knobs, read per call so that one process can sweep them
   const char* env_t = getenv("MOT_AR_THREADS");
   const char* env_u = getenv("MOT_AR_UNROLL");
   int threads = env_t ? atoi(env_t) : kArThreads;
   if (threads < 32 || threads > 1024 || threads % 32) threads = kArThreads;
-  const int unroll = env_u ? atoi(env_u) : 8;
-  long long max_blocks = env_b ? atoi(env_b) : kArMaxBlocks;
+  const int unroll = env_u ? atoi(env_u) : (algo == MOT_DP_NVLS ? 8 : 4);
+  if (threads > 512 && (algo == MOT_DP_P2P || unroll > 8)) threads = 512;   // those kernels are compiled for 512 threads
+  long long max_blocks = env_b ? atoi(env_b) : (algo == MOT_DP_NVLS ? kArMaxBlocksNvls : kArMaxBlocksP2p);
   if (max_blocks < 1) max_blocks = 1;
-  if (max_blocks * world * 4 > 9216) max_blocks = 9216 / (world * 4);   // signal-pad slots
-  long long blocks = (n_vec / world + threads * 8 - 1) / (threads * 8);
+  if (max_blocks * world > kPadSlots) max_blocks = kPadSlots / world;   // signal-pad slots: blocks x world uint32
+  long long blocks = (n_vec / world + threads * 4 - 1) / (threads * 4);
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads_dev);
-  char* mc = reinterpret_cast<char*>(multicast_ptr);
   const dim3 g((unsigned)blocks), b(threads);
-  if (dtype == MOT_BF16) {
-    if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, n_vec, epoch);
-    else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, n_vec, epoch);
+  const bool bf = dtype == MOT_BF16;
+  const int lastf = last ? 1 : 0;
+  if (algo == MOT_DP_NVLS) {
+    char* mc = reinterpret_cast<char*>(multicast_ptr);
+    if (bf) {
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+      else if (unroll == 16) launch_pdl(nvls_allreduce_avg_kernel<true, 16>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+      else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+    } else {
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+      else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+    }
   } else {
-    if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, n_vec, epoch);
-    else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, n_vec, epoch);
+    char* const* peers = reinterpret_cast<char* const*>(peer_ptrs_dev);
+    if (world == 2) {
+      if (bf) launch_p2p<true, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      else launch_p2p<false, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+    } else if (world == 4) {
+      if (bf) launch_p2p<true, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      else launch_p2p<false, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+    } else {
+      if (bf) launch_p2p<true, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      else launch_p2p<false, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+    }
   }
   count_launch();
   return check_launch();
+}
+
+// The whole bucket in one call (round-1 entry point): one range, both barriers.  `epoch` grows by TWO per call.
+extern "C" int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
+                                    int32_t dtype, uint32_t epoch, void* stream) {
+  if (!multicast_ptr) return MOT_ERR_BAD_ARG;
+  return mot_dp_exchange(multicast_ptr, nullptr, signal_pads_dev, rank, world, 0, n_bytes, dtype, epoch, 1, MOT_DP_NVLS, stream);
 }

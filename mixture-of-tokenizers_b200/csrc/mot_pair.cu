@@ -298,6 +298,7 @@ extern "C" int mot_byte_pair_bwd(const void* ids_a, const void* ids_b, int32_t i
   q.combine = MOT_BYTES_ONLY;
   q.N = n_tokens; q.R = 32; q.Vb = byte_vocab; q.bd = byte_dim; q.bpt = bpt; q.Do = bpt * byte_dim;
   q.n_rep = kByteRep; q.byte_acc = p.acc; q.E_byte = E_byte; q.gE_byte = gE_byte; q.eps = eps;
+  q.last_slab = 1;  // the byte rows are this launch's only work
   const int fb = (byte_vocab + 7) / 8;
   return dtype == MOT_BF16 ? launch_finalize_bf16(q, fb, s) : launch_finalize_f32(q, fb, s);
 }

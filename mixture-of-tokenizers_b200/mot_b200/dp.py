@@ -29,34 +29,57 @@ def broadcast_params(params: Iterable[torch.Tensor], src: int = 0, group=None) -
         dist.broadcast(p.detach(), src, group=group)
 
 
-def own_allreduce_pays(group=None) -> bool:
-    """Whether the library's NVLS all-reduce beats NCCL for the gradient bucket of this path (77 MB bf16 at the
-    124M shape).  Measured on 8xB200 / NVSwitch (profiles/r1_experiments.md): 8 ranks 215 us vs NCCL 270 us;
-    4 ranks 235 vs 214 us; 2 ranks 226 vs 174 us.  Through the switch every rank moves S*(1 + 1/n) bytes per
-    direction (its own slice also travels to the switch and back), NCCL's ring 2*S*(n-1)/n: the in-switch reduction
-    wins from n = 8 on.  MOT_DP_OWN=1 / MOT_DP_NCCL=1 force either."""
+def pick_algo(world: int, has_multicast: bool) -> str:
+    """Which exchange runs the gradient bucket of this path (77 MB bf16 at the 124M shape) at `world` ranks of one
+    NVSwitch node.  Per GPU and direction the in-switch reduction (NVLS) moves S (1 + 1/n) bytes, the peer-to-peer
+    two-shot 2 S (n - 1) / n: P2P is less at n = 2, NVLS from n = 4 on; NCCL remains for everything else (no symmetric
+    memory, other world sizes).  Measured on 8 x B200: profiles/r2_dp.md.  MOT_DP_ALGO=nvls|p2p|nccl forces one."""
+    forced = os.environ.get("MOT_DP_ALGO", "").lower()
     if os.environ.get("MOT_DP_NCCL"):
-        return False
-    if os.environ.get("MOT_DP_OWN"):
-        return True
-    if not (dist.is_available() and dist.is_initialized()):
-        return False
-    return dist.get_world_size(group) >= 8
+        forced = "nccl"
+    if forced in ("nvls", "p2p", "nccl"):
+        if forced == "nvls" and not has_multicast:
+            return "nccl"
+        if forced == "p2p" and world not in (2, 4, 8):
+            return "nccl"
+        return forced
+    if world == 2:
+        return "p2p"
+    if has_multicast and world >= 3:
+        return "nvls"
+    if world in (4, 8):
+        return "p2p"
+    return "nccl"
+
+
+_DP_STREAMS: dict = {}
+
+
+def dp_stream(dev) -> torch.cuda.Stream:
+    """Per-device stream on which the exchange kernels run beside the backward (high priority: its few CTAs should get
+    their SMs as soon as a slab is ready)."""
+    st = _DP_STREAMS.get(dev.index)
+    if st is None:
+        st = _DP_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    return st
 
 
 class GradBucket:
     """One flat buffer holding the gradients of `params` back to back (each slice 16-byte aligned), with a view per
     parameter.  `views()` are handed to the backward kernels as their dense-gradient outputs (mot_embed_bwd
     overwrites every row, so no zeroing is needed), `attach()` points `param.grad` at them, `all_reduce_avg()`
-    averages the whole bucket across ranks in one collective."""
+    averages the whole bucket across ranks in one collective.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric=False,
-                 group=None):
-        """symmetric=True (CUDA, initialised NCCL group): allocate the bucket in symmetric memory with a multicast
-        mapping so that all_reduce_avg() runs the library's own NVLS kernel (mot_dp_allreduce_avg) instead of NCCL.
-        symmetric="auto": do that where the kernel was measured faster than NCCL (own_allreduce_pays)."""
-        if symmetric == "auto":
-            symmetric = own_allreduce_pays(group)
+    With symmetric memory (CUDA, NVLink peers) the exchange is the library's own kernel (`mot_dp_exchange`: NVLS
+    in-switch reduction or peer-to-peer two-shot) and can run as a PIPELINE beside the backward: the backward walks the
+    vocabulary in `n_slabs` slabs (mot_embed_bwd_slab), `exchange_async(lo, hi, last)` averages the rows of a finished
+    slab on a second stream while the next slab is computed, `wait()` joins.  This is the overlap the reference gets
+    from its asynchronous per-parameter all-reduces (runs/7:697-711), inside the path."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric="auto",
+                 group=None, n_slabs: int = 4, reserve_sms: int = 8):
+        """symmetric=True / "auto" (CUDA, initialised process group with more than one rank): allocate the bucket in
+        symmetric memory so that the library's own exchange kernels apply; False: ordinary memory, NCCL."""
         self.params: List[torch.nn.Parameter] = list(params)
         if not self.params:
             raise ValueError("GradBucket needs at least one parameter")
@@ -71,24 +94,32 @@ class GradBucket:
             self.offsets.append(n)
             n += (p.numel() + align - 1) // align * align
         self._symm = None
-        self._epoch = 0
+        self._epoch = 1
+        self.algo = "nccl"
+        self.n_slabs = 1
+        self.reserve_sms = int(reserve_sms)
+        self._ev = None
+        self._pending = False
         n = (n + align - 1) // align * align
         self.flat = None
-        if symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() \
-                and not os.environ.get("MOT_DP_NCCL"):
-            # Symmetric memory + multicast need NVSwitch and a driver with fabric support; where either is missing
-            # the bucket is ordinary device memory and the exchange is NCCL's all-reduce (a library collective on
-            # the same data, not a different code path for the kernels).
+        have_group = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size(group) if have_group else 1
+        if symmetric and dev.type == "cuda" and have_group and world > 1 and group is None \
+                and self.dtype in (torch.bfloat16, torch.float32) and pick_algo(world, True) != "nccl":
+            # Symmetric memory needs NVLink peers (and NVSwitch multicast for NVLS) and a driver with fabric support; where
+            # it is missing the bucket is ordinary device memory and the exchange is NCCL's all-reduce (a library
+            # collective on the same data, not a different code path for the kernels).
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                grp = group if group is not None else dist.group.WORLD
                 flat = symm_mem.empty(n, dtype=self.dtype, device=dev)
                 flat.zero_()
-                hdl = symm_mem.rendezvous(flat, grp)
-                self.flat = flat
-                if hdl.multicast_ptr != 0:       # NVSwitch multicast (NVLS) available
-                    self._symm = hdl
-            except Exception as e:  # noqa: BLE001 - any allocator / rendezvous failure means "no NVLS here"
+                hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+                algo = pick_algo(world, hdl.multicast_ptr != 0)
+                if algo != "nccl":
+                    self.flat, self._symm, self.algo = flat, hdl, algo
+                    self.n_slabs = max(1, int(os.environ.get("MOT_DP_SLABS", n_slabs)))
+                    self._ev = torch.cuda.Event()
+            except Exception as e:  # noqa: BLE001 - any allocator / rendezvous failure means "no symmetric memory here"
                 warnings.warn(f"GradBucket: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL")
                 self.flat = None
                 self._symm = None
@@ -96,6 +127,7 @@ class GradBucket:
             self.flat = torch.zeros(n, dtype=self.dtype, device=dev)
         self._views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
 
+    # ------------------------------------------------------------------------------------------------ views
     def views(self) -> List[torch.Tensor]:
         return self._views
 
@@ -103,6 +135,12 @@ class GradBucket:
         for p, v in zip(self.params, self._views):
             if p is param:
                 return v
+        raise KeyError("parameter is not in this bucket")
+
+    def offset_of(self, param: torch.nn.Parameter) -> int:
+        for p, o in zip(self.params, self.offsets):
+            if p is param:
+                return o
         raise KeyError("parameter is not in this bucket")
 
     def attach(self) -> None:
@@ -115,22 +153,62 @@ class GradBucket:
                 v.copy_(p.grad)
             p.grad = v
 
+    # ------------------------------------------------------------------------------------------------ exchange
+    @property
+    def pipelined(self) -> bool:
+        """The exchange can run slab by slab beside the backward (own kernels over symmetric memory)."""
+        return self._symm is not None and self.n_slabs > 1
+
+    def _exchange(self, lo: int, hi: int, last: bool, stream: int) -> None:
+        from . import _lib as L
+        h = self._symm
+        esz = self.flat.element_size()
+        rc = L.lib().mot_dp_exchange(h.multicast_ptr if self.algo == "nvls" else None,
+                                     h.buffer_ptrs_dev if self.algo == "p2p" else None, h.signal_pad_ptrs_dev, h.rank,
+                                     h.world_size, lo * esz, (hi - lo) * esz,
+                                     L.BF16 if self.dtype == torch.bfloat16 else L.F32, self._epoch, 1 if last else 0,
+                                     L.DP_NVLS if self.algo == "nvls" else L.DP_P2P, stream)
+        L.check(rc, "mot_dp_exchange")
+        self._epoch = (self._epoch + (2 if last else 1)) & 0xFFFFFFFF
+
+    def exchange_async(self, lo: int, hi: int, last: bool) -> None:
+        """Average elements [lo, hi) of the bucket (multiples of 16 bytes) across ranks on the exchange stream, ordered
+        after everything queued on the current stream (the backward of that slab).  Every rank issues the same calls;
+        the final range of a step passes last=True.  `wait()` joins the exchange stream into the current one."""
+        if self._symm is None:
+            raise RuntimeError("GradBucket.exchange_async needs the symmetric-memory bucket (own exchange kernels)")
+        dev = self.flat.device
+        cur = torch.cuda.current_stream(dev)
+        side = dp_stream(dev)
+        self._ev.record(cur)
+        side.wait_event(self._ev)
+        with torch.cuda.device(dev):
+            self._exchange(lo, hi, last, side.cuda_stream)
+        self._pending = True
+
+    def wait(self) -> None:
+        """The current stream waits for the exchange stream (no host synchronisation)."""
+        if self._pending:
+            dev = self.flat.device
+            torch.cuda.current_stream(dev).wait_stream(dp_stream(dev))
+            self._pending = False
+
     def all_reduce_avg(self, group=None, async_op: bool = False):
-        """One collective for the whole bucket.  AVG = SUM / world_size (gloo has no AVG reduce op)."""
+        """Average the whole bucket across ranks.  AVG = SUM / world_size (gloo has no AVG reduce op).  If the backward
+        already exchanged its slabs (exchange_async) this only joins the exchange stream."""
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world = dist.get_world_size(group)
-        if self._symm is not None and group is None and self.dtype in (torch.bfloat16, torch.float32):
-            # one kernel per rank over the multicast mapping: reduce in the switch, average, multicast back
-            from . import _lib as L
-            h = self._symm
-            self._epoch += 1
+        if self._symm is not None:
+            if async_op or group is not None:
+                raise NotImplementedError("GradBucket: the symmetric-memory exchange is stream-ordered on the whole world "
+                                          "(async_op / sub-groups are NCCL features: build the bucket with symmetric=False)")
+            if self._pending:          # the slabs are already in flight on the exchange stream
+                self.wait()
+                return None
             dev = self.flat.device
-            rc = L.lib().mot_dp_allreduce_avg(h.multicast_ptr, h.signal_pad_ptrs_dev, h.rank, h.world_size,
-                                              self.flat.numel() * self.flat.element_size(),
-                                              L.BF16 if self.dtype == torch.bfloat16 else L.F32, self._epoch,
-                                              torch.cuda.current_stream(dev).cuda_stream)
-            L.check(rc, "mot_dp_allreduce_avg")
+            with torch.cuda.device(dev):
+                self._exchange(0, self.flat.numel(), True, torch.cuda.current_stream(dev).cuda_stream)
             return None
         if dist.get_backend(group) == "nccl":
             return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)

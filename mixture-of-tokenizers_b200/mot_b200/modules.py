@@ -88,7 +88,7 @@ class MoTEmbedding(nn.Module):
         b = self.grad_bucket
         tw = self.embed_tokens.weight if self.embed_tokens is not None else None
         bw = self.embed_bytes.weight if self.embed_bytes is not None else None
-        return ((tw, b.view_of(tw)) if tw is not None else None, (bw, b.view_of(bw)) if bw is not None else None)
+        return ((tw, b.view_of(tw)) if tw is not None else None, (bw, b.view_of(bw)) if bw is not None else None, b)
 
 
 # variant name -> MixSpec kwargs of the concat + dense projection family

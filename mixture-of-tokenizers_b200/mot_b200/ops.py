@@ -413,6 +413,16 @@ class _MotEmbedFn(torch.autograd.Function):
             raise NotImplementedError("mot_b200: token and byte tables must share one dtype")
         lam_c = lam.detach().to(torch.float32).contiguous() if lam is not None else None
         desc = make_desc(spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=ttb, has_lam=lam is not None, seq_len=seq_len)
+        # data-parallel pipeline: a bucket that holds exactly [token table | byte table] in symmetric memory lets the
+        # backward run as vocabulary slabs with the exchange of slab k beside the backward of slab k + 1
+        ctx.dp_bucket = None
+        bucket = grad_bufs[2] if grad_bufs is not None and len(grad_bufs) > 2 else None
+        if bucket is not None and bucket.pipelined and n > 0 and E_tok is not None and E_byte is not None \
+                and len(bucket.params) == 2 and bucket.params[0] is grad_bufs[0][0] and bucket.params[1] is grad_bufs[1][0] \
+                and bool(L.lib().mot_embed_bwd_uses_saved(desc)):
+            desc = make_desc(spec, n, E_tok_c, E_byte_c, bpt, ids=ids, ttb=ttb, has_lam=lam is not None, seq_len=seq_len,
+                             dp_slabs=bucket.n_slabs)
+            ctx.dp_bucket = bucket
         ref = E_tok_c if E_tok_c is not None else E_byte_c
         out = torch.empty((n, desc.out_dim), dtype=ref.dtype, device=dev)
         # the backward needs the positions grouped by token id: start that sort now, beside the forward kernel
@@ -469,8 +479,22 @@ class _MotEmbedFn(torch.autograd.Function):
             clean = True          # the plan ran on a clean (or freshly cleared) workspace and leaves it clean
         else:
             clean, ws.clean = ws.clean, False
-        embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
-                           plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd, plan_joined=planned)
+        bucket = ctx.dp_bucket
+        if bucket is not None and direct[0] is not None and direct[1] is not None and out_saved is not None \
+                and not torch.cuda.is_current_stream_capturing():
+            # slab k of the vocabulary, then its rows of the bucket go to the exchange stream while slab k + 1 is computed;
+            # the byte table (finished by the last slab) travels with the last range.  bucket.all_reduce_avg() / wait() joins.
+            K, V_, Dt_ = bucket.n_slabs, E_tok.shape[0], E_tok.shape[1]
+            for k in range(K):
+                embed_backward_slab_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, out_saved, rstd, gE_tok, gE_byte, g_lam,
+                                        ws.buf, k, K, reserve_sms=bucket.reserve_sms if k > 0 else 0,
+                                        plan_ready=planned or k > 0, ws_clean=clean or k > 0, plan_joined=planned, stream=st)
+                lo, hi = slab_rows(V_, k, K)
+                bucket.exchange_async(lo * Dt_, hi * Dt_ if k < K - 1 else bucket.flat.numel(), last=(k == K - 1))
+        else:
+            embed_backward_out(desc, tok, ids, ttb, E_tok, E_byte, lam, g, gE_tok, gE_byte, g_lam, ws.buf,
+                               plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd,
+                               plan_joined=planned)
         ws.clean = True           # every completed backward leaves the head of the workspace zeroed
         ctx.ws = None
         release_workspace(ws)

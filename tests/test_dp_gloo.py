@@ -36,10 +36,11 @@ def _worker(rank, world, port, q):
         mine = dp.shard_for_rank(stream, pos=100, local=64, rank=rank)
         assert mine[0].item() == 100 + rank * 64 and mine.numel() == 64
         # one flat bucket, per-parameter views, one collective
-        # "auto": the own NVLS all-reduce only from 8 ranks up (measured), never without CUDA + multicast
-        assert dp.own_allreduce_pays() is False
+        # "auto": the own exchange kernels need CUDA + symmetric memory; on CPU / gloo the bucket is ordinary memory
+        assert dp.pick_algo(2, False) == "p2p" and dp.pick_algo(8, True) == "nvls" and dp.pick_algo(4, True) == "nvls"
+        assert dp.pick_algo(4, False) == "p2p" and dp.pick_algo(3, False) == "nccl" and dp.pick_algo(6, True) == "nvls"
         bucket = dp.GradBucket([E_tok, E_byte], symmetric="auto")
-        assert bucket._symm is None
+        assert bucket._symm is None and bucket.algo == "nccl" and not bucket.pipelined
         v_tok, v_byte = bucket.views()
         assert v_tok.shape == E_tok.shape and v_byte.shape == E_byte.shape
         assert v_tok.data_ptr() == bucket.flat.data_ptr() and bucket.offsets[1] % 4 == 0
@@ -48,6 +49,9 @@ def _worker(rank, world, port, q):
         bucket.attach()
         assert E_tok.grad.data_ptr() == v_tok.data_ptr()
         bucket.all_reduce_avg()
+        bucket.wait()                                      # nothing pending: a no-op
+        with pytest.raises(RuntimeError):
+            bucket.exchange_async(0, 16, True)             # the pipelined exchange exists only over symmetric memory
         assert torch.allclose(E_tok.grad, torch.full_like(E_tok, 1.5))      # mean of 1, 2
         assert torch.allclose(E_byte.grad, torch.full_like(E_byte, 15.0))   # mean of 10, 20
         # a gradient produced outside the bucket is copied in by attach()
