@@ -68,10 +68,13 @@ __device__ __forceinline__ void scale_vec(uint32_t (&r)[4], float inv, bool bf16
 template <bool BF16, int kUnroll>
 __global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_kernel(char* mc, uint32_t* const* pads, int rank, int world,
                                                                         long long vec_lo, long long n_vec /* 16-byte vectors */,
-                                                                        uint32_t epoch, int last) {
+                                                                        uint32_t epoch, int last, long long* trace) {
   pdl_launch_dependents();
+  MOT_STAMP(trace, blockIdx.x, 0);
   pdl_wait();  // the local backward / finalize kernels of this range have completed: this rank's copy is final
+  MOT_STAMP(trace, blockIdx.x, 1);
   rank_barrier(pads, rank, world, epoch);
+  MOT_STAMP(trace, blockIdx.x, 2);
   const long long per = (n_vec + world - 1) / world;
   const long long lo = vec_lo + per * rank, hi = min(lo + per, vec_lo + n_vec);
   const float inv = 1.f / (float)world;
@@ -104,7 +107,9 @@ __global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_k
       }
     }
   }
+  MOT_STAMP(trace, blockIdx.x, 3);
   if (last) rank_barrier(pads, rank, world, epoch + 1u);
+  MOT_STAMP(trace, blockIdx.x, 4);
 }
 
 __device__ __forceinline__ void ld_sys_16(const char* p, uint32_t (&r)[4]) {
@@ -118,10 +123,14 @@ __device__ __forceinline__ void st_sys_16(char* p, const uint32_t (&r)[4]) {
 // flight per thread (an NVLink round trip is about 2 us: a rank needs megabytes outstanding to fill 900 GB/s).
 template <bool BF16, int WORLD, int kUnroll>
 __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* peers, uint32_t* const* pads, int rank,
-                                                                       long long vec_lo, long long n_vec, uint32_t epoch, int last) {
+                                                                       long long vec_lo, long long n_vec, uint32_t epoch, int last,
+                                                                       long long* trace) {
   pdl_launch_dependents();
+  MOT_STAMP(trace, blockIdx.x, 0);
   pdl_wait();
+  MOT_STAMP(trace, blockIdx.x, 1);
   rank_barrier(pads, rank, WORLD, epoch);
+  MOT_STAMP(trace, blockIdx.x, 2);
   char* P[WORLD];
 #pragma unroll
   for (int q = 0; q < WORLD; ++q) P[q] = peers[q];
@@ -168,18 +177,20 @@ __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* pee
       }
     }
   }
+  MOT_STAMP(trace, blockIdx.x, 3);
   if (last) rank_barrier(pads, rank, WORLD, epoch + 1u);
+  MOT_STAMP(trace, blockIdx.x, 4);
 }
 
 template <bool BF16, int WORLD>
 static void launch_p2p(int unroll, dim3 g, dim3 b, cudaStream_t s, char* const* peers, uint32_t* const* pads, int rank,
-                       long long vec_lo, long long n_vec, uint32_t epoch, int last) {
+                       long long vec_lo, long long n_vec, uint32_t epoch, int last, long long* trace) {
   if (unroll >= 4 && WORLD <= 4)
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 4>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 4>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
   else if (unroll >= 2 && WORLD <= 8)
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 2>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 2>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
   else
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
 }
 
 }  // namespace mot
@@ -219,27 +230,31 @@ extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, 
   const dim3 g((unsigned)blocks), b(threads);
   const bool bf = dtype == MOT_BF16;
   const int lastf = last ? 1 : 0;
+  // MOT_TRACE builds: block stamps of consecutive exchange launches go to consecutive 64-block regions behind the
+  // forward / backward / finalize regions of the trace buffer
+  static int trace_seq = 0;
+  long long* trace = g_trace ? g_trace + (3 * 4096 + (size_t)(trace_seq++ % 16) * 64) * 64 : nullptr;
   if (algo == MOT_DP_NVLS) {
     char* mc = reinterpret_cast<char*>(multicast_ptr);
     if (bf) {
-      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
-      else if (unroll == 16) launch_pdl(nvls_allreduce_avg_kernel<true, 16>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
-      else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
+      else if (unroll == 16) launch_pdl(nvls_allreduce_avg_kernel<true, 16>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
+      else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
     } else {
-      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
-      else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf);
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
+      else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
     }
   } else {
     char* const* peers = reinterpret_cast<char* const*>(peer_ptrs_dev);
     if (world == 2) {
-      if (bf) launch_p2p<true, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
-      else launch_p2p<false, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      if (bf) launch_p2p<true, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      else launch_p2p<false, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
     } else if (world == 4) {
-      if (bf) launch_p2p<true, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
-      else launch_p2p<false, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      if (bf) launch_p2p<true, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      else launch_p2p<false, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
     } else {
-      if (bf) launch_p2p<true, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
-      else launch_p2p<false, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf);
+      if (bf) launch_p2p<true, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      else launch_p2p<false, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
     }
   }
   count_launch();
