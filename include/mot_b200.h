@@ -261,6 +261,7 @@ int mot_byte_pair_bwd(const void* ids_a, const void* ids_b, int32_t ids_i64, int
  *   multicast_ptr    : this rank's multicast mapping of all copies (NVLS), or NULL
  *   peer_ptrs_dev    : device array of `world` pointers, entry q = rank q's copy as addressable from this rank (P2P), or NULL
  *   signal_pads_dev  : device array of `world` pointers to the ranks' zero-initialised uint32 signal pads (>= 9216 bytes)
+ *   work_area        : 256 bytes of ordinary device memory of this rank, zero-initialised once (tile counters of the launches)
  * mot_dp_exchange averages the byte range [byte_offset, byte_offset + n_bytes) of the bucket in place on every rank
  * (both multiples of 16).  Every rank makes the same sequence of calls.  `epoch` is the caller's barrier counter: the
  * call uses `epoch` for its entry barrier and, when `last` != 0, `epoch + 1` for an exit barrier -- so it grows by 1
@@ -270,13 +271,13 @@ int mot_byte_pair_bwd(const void* ids_a, const void* ids_b, int32_t ids_i64, int
  *   algo MOT_DP_NVLS : multimem.ld_reduce / multimem.st through the multicast mapping (reduction inside the switch)
  *        MOT_DP_P2P  : loads / stores through the peer pointers, fp32 accumulation in rank order (world 2, 4 or 8) */
 enum { MOT_DP_NVLS = 0, MOT_DP_P2P = 1 };
-int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, int32_t rank,
-                    int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch, int32_t last,
-                    int32_t algo, void* stream);
+int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
+                    int32_t rank, int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch,
+                    int32_t last, int32_t algo, void* stream);
 /* The whole bucket as one NVLS range with both barriers (= mot_dp_exchange(..., 0, n_bytes, ..., last = 1, MOT_DP_NVLS)):
  * `epoch` grows by 2 per call. */
-int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
-                         int32_t dtype, uint32_t epoch, void* stream);
+int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, void* work_area, int32_t rank, int32_t world,
+                         int64_t n_bytes, int32_t dtype, uint32_t epoch, void* stream);
 
 /* ---- byte pull across tokens ------------------------------------------------------------------------------
  * Replaces pull_from_left / pull_from_right (spt/data_creation.py:179-305 / :71-176, runs/7:351-428).

@@ -68,24 +68,35 @@ __device__ __forceinline__ void scale_vec(uint32_t (&r)[4], float inv, bool bf16
 template <bool BF16, int kUnroll>
 __global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_kernel(char* mc, uint32_t* const* pads, int rank, int world,
                                                                         long long vec_lo, long long n_vec /* 16-byte vectors */,
-                                                                        uint32_t epoch, int last, long long* trace) {
+                                                                        uint32_t epoch, int last, unsigned* work, long long* trace) {
   pdl_launch_dependents();
   MOT_STAMP(trace, blockIdx.x, 0);
   pdl_wait();  // the local backward / finalize kernels of this range have completed: this rank's copy is final
   MOT_STAMP(trace, blockIdx.x, 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) work[(epoch + 1u) & 63u] = work[(epoch + 2u) & 63u] = 0u;
+  work += epoch & 63u;
   rank_barrier(pads, rank, world, epoch);
   MOT_STAMP(trace, blockIdx.x, 2);
   const long long per = (n_vec + world - 1) / world;
   const long long lo = vec_lo + per * rank, hi = min(lo + per, vec_lo + n_vec);
   const float inv = 1.f / (float)world;
-  // kUnroll independent 16-byte reductions in flight per thread: one switch round trip is microseconds, the link wants
-  // megabytes outstanding
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
+  // The sub-slice is handed out in tiles of blockDim x kUnroll vectors by a counter (work[0], zeroed by the launch): the
+  // CTAs do not run at the same speed (8 ranks, 77 MB, static split: the first CTA finishes at 122 us, the last at 161 us;
+  // profiles/r2_dp.md) and the slowest one sets the exit barrier.  kUnroll independent 16-byte reductions are in flight per
+  // thread: one switch round trip is microseconds, the link wants megabytes outstanding.
+  __shared__ long long tile_s[2];
+  const long long tile_vecs = (long long)blockDim.x * kUnroll;
+  if (threadIdx.x == 0) tile_s[0] = (long long)atomicAdd(work, 1u);
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const long long base = lo + tile_s[it & 1] * tile_vecs;
+    if (base >= hi) break;
+    if (threadIdx.x == 0) tile_s[(it + 1) & 1] = (long long)atomicAdd(work, 1u);  // the next ticket travels while this tile moves
+    const long long i0 = base + threadIdx.x;
     uint32_t r[kUnroll][4];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const long long i = i0 + u * stride;
+      const long long i = i0 + (long long)u * blockDim.x;
       if (i < hi) {
         char* a = mc + i * 16;
         if (BF16)
@@ -98,7 +109,7 @@ __global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_k
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const long long i = i0 + u * stride;
+      const long long i = i0 + (long long)u * blockDim.x;
       if (i < hi) {
         scale_vec(r[u], inv, BF16);
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 16), "r"(r[u][0]), "r"(r[u][1]),
@@ -106,6 +117,7 @@ __global__ void __launch_bounds__(kUnroll > 8 ? 512 : 1024) nvls_allreduce_avg_k
                      : "memory");
       }
     }
+    __syncthreads();
   }
   MOT_STAMP(trace, blockIdx.x, 3);
   if (last) rank_barrier(pads, rank, world, epoch + 1u);
@@ -124,11 +136,13 @@ __device__ __forceinline__ void st_sys_16(char* p, const uint32_t (&r)[4]) {
 template <bool BF16, int WORLD, int kUnroll>
 __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* peers, uint32_t* const* pads, int rank,
                                                                        long long vec_lo, long long n_vec, uint32_t epoch, int last,
-                                                                       long long* trace) {
+                                                                       unsigned* work, long long* trace) {
   pdl_launch_dependents();
   MOT_STAMP(trace, blockIdx.x, 0);
   pdl_wait();
   MOT_STAMP(trace, blockIdx.x, 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) work[(epoch + 1u) & 63u] = work[(epoch + 2u) & 63u] = 0u;
+  work += epoch & 63u;
   rank_barrier(pads, rank, WORLD, epoch);
   MOT_STAMP(trace, blockIdx.x, 2);
   char* P[WORLD];
@@ -137,12 +151,19 @@ __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* pee
   const long long per = (n_vec + WORLD - 1) / WORLD;
   const long long lo = vec_lo + per * rank, hi = min(lo + per, vec_lo + n_vec);
   const float inv = 1.f / (float)WORLD;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
+  __shared__ long long tile_s[2];
+  const long long tile_vecs = (long long)blockDim.x * kUnroll;
+  if (threadIdx.x == 0) tile_s[0] = (long long)atomicAdd(work, 1u);
+  __syncthreads();
+  for (int it = 0;; ++it) {  // tiles handed out by a counter, like the NVLS kernel
+    const long long base = lo + tile_s[it & 1] * tile_vecs;
+    if (base >= hi) break;
+    if (threadIdx.x == 0) tile_s[(it + 1) & 1] = (long long)atomicAdd(work, 1u);
+    const long long i0 = base + threadIdx.x;
     uint32_t v[kUnroll][WORLD][4];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const long long i = i0 + u * stride;
+      const long long i = i0 + (long long)u * blockDim.x;
       if (i < hi) {
 #pragma unroll
         for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + i * 16, v[u][q]);
@@ -150,7 +171,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* pee
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const long long i = i0 + u * stride;
+      const long long i = i0 + (long long)u * blockDim.x;
       if (i < hi) {
         uint32_t r[4];
 #pragma unroll
@@ -176,6 +197,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* pee
         for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + i * 16, r);
       }
     }
+    __syncthreads();
   }
   MOT_STAMP(trace, blockIdx.x, 3);
   if (last) rank_barrier(pads, rank, WORLD, epoch + 1u);
@@ -184,23 +206,23 @@ __global__ void __launch_bounds__(512) p2p_allreduce_avg_kernel(char* const* pee
 
 template <bool BF16, int WORLD>
 static void launch_p2p(int unroll, dim3 g, dim3 b, cudaStream_t s, char* const* peers, uint32_t* const* pads, int rank,
-                       long long vec_lo, long long n_vec, uint32_t epoch, int last, long long* trace) {
+                       long long vec_lo, long long n_vec, uint32_t epoch, int last, unsigned* work, long long* trace) {
   if (unroll >= 4 && WORLD <= 4)
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 4>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 4>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, work, trace);
   else if (unroll >= 2 && WORLD <= 8)
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 2>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 2>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, work, trace);
   else
-    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, trace);
+    launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, work, trace);
 }
 
 }  // namespace mot
 
 using namespace mot;
 
-extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, int32_t rank,
-                               int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch, int32_t last,
-                               int32_t algo, void* stream) {
-  if (!signal_pads_dev || world < 1 || rank < 0 || rank >= world || n_bytes < 0 || byte_offset < 0) return MOT_ERR_BAD_ARG;
+extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
+                               int32_t rank, int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch,
+                               int32_t last, int32_t algo, void* stream) {
+  if (!signal_pads_dev || !work_area || world < 1 || rank < 0 || rank >= world || n_bytes < 0 || byte_offset < 0) return MOT_ERR_BAD_ARG;
   if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
   if (algo == MOT_DP_NVLS && !multicast_ptr) return MOT_ERR_BAD_ARG;
   if (algo == MOT_DP_P2P && !peer_ptrs_dev) return MOT_ERR_BAD_ARG;
@@ -232,29 +254,32 @@ extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, 
   const int lastf = last ? 1 : 0;
   // MOT_TRACE builds: block stamps of consecutive exchange launches go to consecutive 64-block regions behind the
   // forward / backward / finalize regions of the trace buffer
+  // tile counter of this launch: word (epoch mod 64) of the caller's zero-initialised work area; every launch zeroes the
+  // two words its successors may use (epoch + 1, epoch + 2), so no memset sits between the kernels of the stream
+  unsigned* work = reinterpret_cast<unsigned*>(work_area);
   static int trace_seq = 0;
   long long* trace = g_trace ? g_trace + (3 * 4096 + (size_t)(trace_seq++ % 16) * 64) * 64 : nullptr;
   if (algo == MOT_DP_NVLS) {
     char* mc = reinterpret_cast<char*>(multicast_ptr);
     if (bf) {
-      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
-      else if (unroll == 16) launch_pdl(nvls_allreduce_avg_kernel<true, 16>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
-      else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<true, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, work, trace);
+      else if (unroll == 16) launch_pdl(nvls_allreduce_avg_kernel<true, 16>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, work, trace);
+      else launch_pdl(nvls_allreduce_avg_kernel<true, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, work, trace);
     } else {
-      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
-      else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, trace);
+      if (unroll == 4) launch_pdl(nvls_allreduce_avg_kernel<false, 4>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, work, trace);
+      else launch_pdl(nvls_allreduce_avg_kernel<false, 8>, g, b, 0, s, mc, pads, (int)rank, (int)world, vec_lo, n_vec, epoch, lastf, work, trace);
     }
   } else {
     char* const* peers = reinterpret_cast<char* const*>(peer_ptrs_dev);
     if (world == 2) {
-      if (bf) launch_p2p<true, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
-      else launch_p2p<false, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      if (bf) launch_p2p<true, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
+      else launch_p2p<false, 2>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
     } else if (world == 4) {
-      if (bf) launch_p2p<true, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
-      else launch_p2p<false, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      if (bf) launch_p2p<true, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
+      else launch_p2p<false, 4>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
     } else {
-      if (bf) launch_p2p<true, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
-      else launch_p2p<false, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, trace);
+      if (bf) launch_p2p<true, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
+      else launch_p2p<false, 8>(unroll, g, b, s, peers, pads, rank, vec_lo, n_vec, epoch, lastf, work, trace);
     }
   }
   count_launch();
@@ -262,8 +287,9 @@ extern "C" int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, 
 }
 
 // The whole bucket in one call (round-1 entry point): one range, both barriers.  `epoch` grows by TWO per call.
-extern "C" int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, int32_t rank, int32_t world, int64_t n_bytes,
-                                    int32_t dtype, uint32_t epoch, void* stream) {
+extern "C" int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, void* work_area, int32_t rank, int32_t world,
+                                    int64_t n_bytes, int32_t dtype, uint32_t epoch, void* stream) {
   if (!multicast_ptr) return MOT_ERR_BAD_ARG;
-  return mot_dp_exchange(multicast_ptr, nullptr, signal_pads_dev, rank, world, 0, n_bytes, dtype, epoch, 1, MOT_DP_NVLS, stream);
+  return mot_dp_exchange(multicast_ptr, nullptr, signal_pads_dev, work_area, rank, world, 0, n_bytes, dtype, epoch, 1, MOT_DP_NVLS,
+                         stream);
 }

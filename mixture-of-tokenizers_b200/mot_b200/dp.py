@@ -52,6 +52,17 @@ def pick_algo(world: int, has_multicast: bool) -> str:
     return "nccl"
 
 
+def default_slabs(world: int) -> int:
+    """Vocabulary slabs of the pipelined step (mot_embed_bwd_slab + exchange_async): 1 = the backward in one piece, then one
+    exchange.  Every extra slab costs a backward launch (ramp + tail, ~8 us) and an exchange launch with its entry
+    barrier and drain (~12 us), and the exchange traffic slows the backward it runs beside.  Measured at 48K tokens /
+    77 MB bucket (profiles/r2_dp.md): 2 ranks 254 / 258 / 274 us per step with 1 / 2 / 4 slabs, 8 ranks 289 / 299 / 328 us:
+    the exchange (150-200 us) is twice the compute step (92 us) and link-bound, so hiding the 52 us backward behind it
+    buys less than the slicing costs.  The default is therefore one piece; MOT_DP_SLABS=n / GradBucket(n_slabs=n) turn
+    the pipeline on (it pays when the compute step is long against the per-slab overheads)."""
+    return 1
+
+
 _DP_STREAMS: dict = {}
 
 
@@ -77,7 +88,7 @@ class GradBucket:
     from its asynchronous per-parameter all-reduces (runs/7:697-711), inside the path."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric="auto",
-                 group=None, n_slabs: int = 4, reserve_sms: int = 8):
+                 group=None, n_slabs: Optional[int] = None, reserve_sms: int = 8):
         """symmetric=True / "auto" (CUDA, initialised process group with more than one rank): allocate the bucket in
         symmetric memory so that the library's own exchange kernels apply; False: ordinary memory, NCCL."""
         self.params: List[torch.nn.Parameter] = list(params)
@@ -117,8 +128,10 @@ class GradBucket:
                 algo = pick_algo(world, hdl.multicast_ptr != 0)
                 if algo != "nccl":
                     self.flat, self._symm, self.algo = flat, hdl, algo
-                    self.n_slabs = max(1, int(os.environ.get("MOT_DP_SLABS", n_slabs)))
+                    self.n_slabs = max(1, int(os.environ.get("MOT_DP_SLABS", n_slabs if n_slabs is not None
+                                                             else default_slabs(world))))
                     self._ev = torch.cuda.Event()
+                    self._work = torch.zeros(64, dtype=torch.int32, device=dev)   # tile counters of the exchange launches
             except Exception as e:  # noqa: BLE001 - any allocator / rendezvous failure means "no symmetric memory here"
                 warnings.warn(f"GradBucket: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL")
                 self.flat = None
@@ -164,7 +177,8 @@ class GradBucket:
         h = self._symm
         esz = self.flat.element_size()
         rc = L.lib().mot_dp_exchange(h.multicast_ptr if self.algo == "nvls" else None,
-                                     h.buffer_ptrs_dev if self.algo == "p2p" else None, h.signal_pad_ptrs_dev, h.rank,
+                                     h.buffer_ptrs_dev if self.algo == "p2p" else None, h.signal_pad_ptrs_dev,
+                                     self._work.data_ptr(), h.rank,
                                      h.world_size, lo * esz, (hi - lo) * esz,
                                      L.BF16 if self.dtype == torch.bfloat16 else L.F32, self._epoch, 1 if last else 0,
                                      L.DP_NVLS if self.algo == "nvls" else L.DP_P2P, stream)
