@@ -50,6 +50,9 @@ WORKLOADS = {
     # scaled-pre-train default (256/48 -> 1024, K = 1024, B=64 x S=1024 per GPU, spt/train_gpt.py:822)
     "mot-proj-runs7-64k": dict(variant="V1", N=65536, Dt=1024, bd=64, bpt=16, Do=1024, dtype="bf16"),
     "mot-proj-spt-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16"),
+    # BASELINE.json configs[3] "16/32 bytes-per-token padding": 32 bytes per token (K = 256 + 32 x 48 = 1792; runs/71072 is
+    # the only reference script with bpt 32, spt/train_gpt.py:922 admits 16/18/20)
+    "mot-proj-spt-bpt32-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=32, Do=1024, dtype="bf16"),
     # scaled-pre-train with --add-padded-and-pulled (spt/train_gpt.py:371-379): two int64 id tensors, rows summed before
     # the per-byte norm (mot_byte_pair_*), same projection
     "mot-proj-spt-addpp-64k": dict(variant="V1", N=65536, Dt=256, bd=48, bpt=16, Do=1024, dtype="bf16", pair=True),
@@ -67,13 +70,14 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "torch-gpu"], default="ours")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--tokens", type=int, default=0, help="override tokens per GPU per step")
     ap.add_argument("--dist", choices=["uniform", "zipf"], default="uniform",
                     help="token id distribution: uniform = the reference's own warm-up generator (runs/7:633-635)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the PyTorch-on-the-same-GPU arm (eager + torch.compile)")
     return ap.parse_args()
 
 
@@ -93,6 +97,19 @@ def algorithmic_bytes(w):
     fwd = N * (4 + 4 * bpt + Dt * e + Do * e) + V_BYTE * bd * e
     bwd = N * (Do * e + 4 + 4 * bpt + Dt * e) + V_TOK * Dt * e + V_BYTE * bd * e
     return fwd, bwd, Do
+
+
+def main_config(w, args, world):
+    """`config` of the JSON line: a pure function of the workload and the launch, identical for --impl ours / reference /
+    torch-gpu (what differs between the arms is reported beside it, never inside it)."""
+    e = 2 if w["dtype"] == "bf16" else 4
+    Do = algorithmic_bytes(w)[2]
+    return {"workload": w["name"], "variant": w["variant"], "tokens_per_gpu_per_step": w["N"], "token_dim": w["Dt"],
+            "byte_dim": w["bd"], "bytes_per_token": w["bpt"], "out_dim": Do, "token_dist": args.dist,
+            "byte_ids": "uniform randint(0,458), given as a tensor (runs/7:635 layout)",
+            "l2": f"working set {(2 * V_TOK * w['Dt'] * e + 2 * w['N'] * Do * e) / 1e6:.0f} MB > 126 MB L2, no flush",
+            "parallelism": f"dp{world}" + (", tables replicated, one exchange (average) of the dense table gradients per step"
+                                           if world > 1 else "")}
 
 
 def make_tokens(N, dist, seed, device="cpu"):
@@ -216,17 +233,25 @@ def cpu_reference_step_fn(w, n_sample, seed=12345):
     if w.get("pair"):
         kw["byte_ids2"] = torch.randint(0, V_BYTE, (1, n_sample * bpt), generator=g, dtype=torch.int32)
 
+    import numpy as np
+    ttb = torch.randint(0, V_BYTE, (V_TOK, max(bpt, 1)), generator=g).to(torch.int16).numpy()   # synthetic table, uniform ids
+
     def step():
-        # the reference computes in the parameter dtype (eager bf16); math_dtype=dt reproduces that cost
-        O.mot_embed_fwd_bwd(spec, toks, ids, E_tok, E_byte, gout, math_dtype=dt, **kw)
+        # the loader's per-step expansion (runs/7:477-485: tokens_to_bytes, then `.view(bpt, -1)` for the sum runs) ...
+        flat = O.tokens_to_bytes(toks.numpy(), ttb)
+        ids_step = torch.from_numpy(np.ascontiguousarray(flat.reshape(bpt, -1) if slot_major else flat).astype(np.int32))
+        # ... and the model front: the reference computes in the parameter dtype (eager bf16); math_dtype=dt reproduces that cost
+        O.mot_embed_fwd_bwd(spec, toks, ids_step if ids_step.shape == ids.shape else ids, E_tok, E_byte, gout, math_dtype=dt, **kw)
     return step
 
 
-def time_cpu_reference(w, steps, warmup, budget_s=20.0):
+def time_cpu_reference(w, steps, warmup, budget_s=20.0, n_sample=None):
+    """The oracle port on the host cores.  n_sample=None: the FULL per-GPU batch of the workload (same config as the GPU
+    arm); the number of timed steps is bounded by `budget_s` seconds."""
     torch.set_num_threads(os.cpu_count() or 1)
-    n_sample = min(w["N"], 8192)
+    n_sample = w["N"] if n_sample is None else min(w["N"], n_sample)
     step = cpu_reference_step_fn(w, n_sample)
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(max(1, min(warmup, 3))):
         step()
     t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
     reps = max(1, min(steps, int(budget_s / max(one, 1e-6))))
@@ -235,25 +260,119 @@ def time_cpu_reference(w, steps, warmup, budget_s=20.0):
         step()
     dt = (time.perf_counter() - t0) / reps
     return {"value": n_sample / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} steps of {n_sample} tokens of the same workload (oracle/mot_oracle.py, eager torch "
-                      f"{w['dtype']} on CPU, fwd+bwd incl. dense [50257,{w['Dt']}] grad)",
-            "ms_per_step": dt * 1e3, "n_sample": n_sample, "steps": reps}
+            "sample": f"{reps} steps of {n_sample} tokens ({'the full per-GPU batch' if n_sample == w['N'] else 'a sample'} of the "
+                      f"same workload): oracle/mot_oracle.py, eager torch {w['dtype']} on CPU, per step: tokens_to_bytes through "
+                      f"the ttb table (runs/7:477-485) + fwd + bwd incl. the dense [50257,{w['Dt']}] gradient",
+            "ms_per_step": dt * 1e3, "n_sample": n_sample, "steps": reps, "warmup": max(1, min(warmup, 3))}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     w = workload_config(args)
-    r = time_cpu_reference(w, args.steps, args.warmup, budget_s=60.0)
+    r = time_cpu_reference(w, args.steps, args.warmup, budget_s=90.0)
+    cfg = main_config(w, args, world) if w["variant"] in ("V3", "V3d", "V4") else \
+        {"workload": w["name"], "variant": w["variant"], "tokens_per_gpu_per_step": w["N"], "token_dim": w["Dt"],
+         "byte_dim": w["bd"], "bytes_per_token": w["bpt"]}
     line = {"impl": "reference", "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": r["value"], "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-            "config": {"workload": w["name"], "variant": w["variant"], "tokens_per_step": r["n_sample"],
-                       "token_dim": w["Dt"], "byte_dim": w["bd"], "bytes_per_token": w["bpt"]},
+            "config": cfg,
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# PyTorch on the same B200: the reference's own lines restated with torch ops on device="cuda" ("the bar is
+# PyTorch 2.11's eager / torch.compile of the same lines on the same B200").  Written out here (not imported from oracle/).
+# ----------------------------------------------------------------------------------------------
+def torch_gpu_step_fn(w, dev, seed=12345):
+    import torch.nn.functional as F
+    g = torch.Generator(device=dev).manual_seed(seed)
+    dt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
+    N, Dt, bd, bpt = w["N"], w["Dt"], w["bd"], w["bpt"]
+    Do = algorithmic_bytes(w)[2]
+    embed_tokens = torch.nn.Embedding(V_TOK, Dt, device=dev, dtype=dt)
+    embed_bytes = torch.nn.Embedding(V_BYTE, bd, device=dev, dtype=dt)
+    tok = torch.randint(0, V_TOK - 1, (N,), generator=g, device=dev, dtype=torch.int32)
+    slot_major = w["variant"].startswith("V3")
+    ids = torch.randint(0, V_BYTE, (bpt, N) if slot_major else (1, N * bpt), generator=g, device=dev, dtype=torch.int32)
+    gout = torch.randn(1, N, Do, generator=g, device=dev).to(dt)
+    scalars = torch.nn.Parameter(torch.tensor([0.5, 0.5], device=dev))
+
+    def norm(x):                                   # runs/71:132-133
+        return F.rms_norm(x, (x.size(-1),))
+
+    def model(token_inputs, byte_inputs):
+        if w["variant"] == "V3":                   # runs/71:228-230,312-314
+            x_toks = embed_tokens(token_inputs)[None]
+            x_bytes = embed_bytes(byte_inputs).squeeze()
+            return norm(x_toks + torch.cat([b for b in x_bytes], dim=-1)[None])
+        if w["variant"] == "V3d":                  # runs/71041:226-228,311-313
+            x_toks = norm(embed_tokens(token_inputs)[None]) * scalars[-1]
+            x_bytes = norm(embed_bytes(byte_inputs).squeeze()) * scalars[-2]
+            return norm(x_toks + torch.cat([b for b in x_bytes], dim=-1)[None])
+        if w["variant"] == "V4":                   # runs/711:224-232,314-316
+            x_toks = embed_tokens(token_inputs)[None]
+            x_bytes = embed_bytes(byte_inputs).squeeze()[None]
+            B, T, _ = x_toks.shape
+            return norm(torch.cat([x_toks, x_bytes.view(B, T, -1)], dim=-1))
+        raise SystemExit(f"torch-gpu arm: no restatement for variant {w['variant']}")
+
+    params = [embed_tokens.weight, embed_bytes.weight] + ([scalars] if w["variant"] == "V3d" else [])
+
+    def make_step(fn):
+        def step():
+            for p_ in params:
+                p_.grad = None
+            fn(tok, ids).backward(gout)
+        return step
+    return make_step(model), make_step(torch.compile(model, dynamic=False)), params
+
+
+def time_torch_gpu(w, dev, steps=20, warmup=5):
+    """ms per fwd+bwd step of the PyTorch restatement, eager and torch.compile(dynamic=False) (the reference's setting,
+    runs/7:623), CUDA-event timed after warm-up (the compile happens in the warm-up)."""
+    eager, compiled, _ = torch_gpu_step_fn(w, dev)
+    out = {"what": "the reference's forward lines restated with torch ops on the same GPU (nn.Embedding gathers, cat, add, "
+                   "F.rms_norm) + autograd backward incl. the dense embedding gradients; inputs resident in HBM",
+           "torch": torch.__version__}
+    for name, fn in (("eager", eager), ("compiled", compiled)):
+        try:
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            out[f"{name}_ms_per_step"] = ms
+            out[f"{name}_tokens_per_sec"] = w["N"] / (ms * 1e-3)
+        except Exception as e:  # noqa: BLE001 - an arm that cannot run is reported, not fatal
+            out[f"{name}_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    return out
+
+
+def run_torch_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    w = workload_config(args)
+    r = time_torch_gpu(w, dev, steps=max(5, min(args.steps, 50)), warmup=max(3, min(args.warmup, 10)))
+    best = min(v for k, v in r.items() if k.endswith("_ms_per_step"))
+    line = {"impl": "torch-gpu", "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": w["N"] / (best * 1e-3), "unit": "tokens/s",
+            "n_gpus": 1, "steps": max(5, min(args.steps, 50)), "warmup": max(3, min(args.warmup, 10)), "ms_per_step": best,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": main_config(w, args, world), "torch_gpu": r, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -548,13 +667,8 @@ def run_ours(args):
             "metric": "byte-mix embedding fwd+bwd tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-            "config": {"workload": w["name"], "variant": w["variant"], "tokens_per_gpu_per_step": N, "token_dim": Dt,
-                       "byte_dim": bd, "bytes_per_token": bpt, "out_dim": Do, "token_dist": args.dist,
-                       "byte_ids": "uniform randint(0,458), given as a tensor (runs/7:635 layout)",
-                       "l2": f"working set {(2 * V_TOK * Dt * esz + 2 * N * Do * esz) / 1e6:.0f} MB > 126 MB L2, no flush",
-                       "parallelism": f"dp{world}" + ((f", flat gradient bucket averaged per step by {bucket.algo}" +
-                                                       (f" in {n_slabs} vocabulary slabs beside the backward" if n_slabs > 1 else " after the backward"))
-                                                      if world > 1 else "")},
+            "config": main_config(w, args, world),
+            "exchange": (f"{bucket.algo}" + (f", {n_slabs} vocabulary slabs beside the backward" if n_slabs > 1 else ", after the backward")) if world > 1 else None,
             "tokens_per_sec_per_gpu": value / world,
             "kernel_ms": {"fwd": fwd_ms, "bwd_main": bwd_ms},
             "step_hbm_gbs": (A_fwd + A_bwd) / (ms_step * 1e-3) / 1e9,
@@ -572,8 +686,10 @@ def run_ours(args):
             line["e2e"] = e2e
         if dp_info is not None:
             line["dp"] = dp_info
+        if world == 1 and not args.no_torch_gpu:
+            line["torch_gpu"] = time_torch_gpu(w, dev)
         if world == 1 and not args.no_cpu_baseline:
-            r = time_cpu_reference(w, steps=50, warmup=2, budget_s=15.0)
+            r = time_cpu_reference(w, steps=50, warmup=2, budget_s=20.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -954,6 +1070,8 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch-gpu":
+        run_torch_gpu(a)
     elif WORKLOADS[a.workload]["variant"] == "V1":
         run_proj(a)
     elif WORKLOADS[a.workload]["variant"] == "V8":

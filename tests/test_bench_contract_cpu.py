@@ -46,3 +46,21 @@ def test_algorithmic_bytes_follow_survey_8d():
     assert fwd == N * (4 + 4 * bpt + Dt * e + Do * e) + Vb * bd * e
     assert bwd == N * (Do * e + 4 + 4 * bpt + Dt * e) + V * Dt * e + Vb * bd * e
     assert abs((fwd + bwd) / 1e6 - 386.0) < 1.0          # the 386 MB per step DESIGN.md quotes
+
+
+def test_arms_share_one_config_dict():
+    """The driver compares the arms' `config`: ours, the CPU reference arm and the PyTorch-on-GPU arm describe the workload
+    with the same dictionary (the full per-GPU batch in every arm)."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    args = argparse.Namespace(dist="uniform")
+    w = dict(bench.WORKLOADS["mot-sum-124M-48k"], name="mot-sum-124M-48k")
+    c1, c2 = bench.main_config(w, args, 1), bench.main_config(w, args, 1)
+    assert c1 == c2 and c1["tokens_per_gpu_per_step"] == 49152 and c1["parallelism"] == "dp1"
+    assert bench.main_config(w, args, 8)["parallelism"].startswith("dp8")
+    r = run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--tokens", "256"])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    w["N"] = 256
+    assert d["config"] == bench.main_config(w, args, 1)                # the reference arm prints exactly that dictionary
+    assert "full per-GPU batch" in d["cpu_baseline"]["sample"] and "tokens_to_bytes" in d["cpu_baseline"]["sample"]
