@@ -886,8 +886,6 @@ def run_proj(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if dp_info is not None:
-            line["dp"] = dp_info
         if world == 1 and not args.no_cpu_baseline:
             r = time_cpu_reference(w, steps=20, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -1,6 +1,9 @@
 // Library plumbing: error strings, launch accounting, device properties.
 #include <atomic>
 #include <mutex>
+#include <csignal>
+#include <cstdio>
+#include <unistd.h>
 
 #include "mot_common.cuh"
 
@@ -10,6 +13,37 @@ thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 static std::atomic<long long> g_launches{0};
 long long* g_trace = nullptr;
 cudaEvent_t g_prof_fwd_start = nullptr, g_prof_fwd_stop = nullptr, g_prof_start = nullptr, g_prof_stop = nullptr;
+
+#ifdef MOT_CHECK
+static long long* g_chk_host = nullptr;
+static void chk_abort_handler(int) {
+  if (g_chk_host && g_chk_host[0]) {
+    char buf[256];
+    int n = snprintf(buf, sizeof buf, "\nMOT_CHECK violation: source line %lld values (%lld, %lld) block %lld thread %lld v_lo<<32|v_hi %lld plan_early %lld R %lld grid %lld\n",
+                     g_chk_host[1], g_chk_host[2], g_chk_host[3], g_chk_host[4], g_chk_host[5], g_chk_host[6], g_chk_host[7] >> 40,
+                     (g_chk_host[7] >> 20) & 0xfffff, g_chk_host[7] & 0xfffff);
+    if (n > 0) (void)!write(2, buf, (size_t)n);
+  }
+  if (g_chk_host) g_chk_host[0] = 0;
+  signal(SIGABRT, SIG_DFL);
+  raise(SIGABRT);
+}
+long long* chk_record() {
+  static long long* dev = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_chk_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+      for (int i = 0; i < 8; ++i) g_chk_host[i] = 0;
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), g_chk_host, 0);
+      signal(SIGABRT, chk_abort_handler);
+      atexit([] { if (g_chk_host && g_chk_host[0]) { signal(SIGABRT, SIG_IGN); chk_abort_handler(0); } });
+    }
+  });
+  return dev;
+}
+#else
+long long* chk_record() { return nullptr; }
+#endif
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

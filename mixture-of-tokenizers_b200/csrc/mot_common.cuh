@@ -18,6 +18,7 @@ void count_launch(int n = 1);
 int check_launch();  // cudaGetLastError -> MOT_OK / MOT_ERR_CUDA
 int device_props(int* sm_count, int* smem_optin);
 // optional event pairs recorded around the main forward / backward kernel (mot_profile_events)
+long long* chk_record();  // MOT_CHECK builds: host-mapped violation record (device pointer), else nullptr
 extern long long* g_trace;  // device buffer for per-warp time stamps (mot_profile_trace; only libraries built with -DMOT_TRACE write it)
 extern cudaEvent_t g_prof_fwd_start, g_prof_fwd_stop, g_prof_start, g_prof_stop;
 
@@ -54,10 +55,57 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 #else
 #define MOT_STAMP(buf, gw, slot) do { } while (0)
 #endif
+// bounds checks of debug builds (-DMOT_CHECK): the first violation is written to a host-mapped record (it survives the
+// dead context; a SIGABRT handler of the check build prints it) and the kernel traps.  Kernels reach the record through
+// their parameter block (`p.chk`).
+#ifdef MOT_CHECK
+#define MOT_ASSERT(cond, what, a, b)                                                                              \
+  do {                                                                                                           \
+    if (!(cond) && p.chk != nullptr) {                                                                           \
+      p.chk[1] = __LINE__; p.chk[2] = (long long)(a); p.chk[3] = (long long)(b);                                 \
+      p.chk[4] = blockIdx.x; p.chk[5] = threadIdx.x; p.chk[6] = ((long long)p.v_lo << 32) | (unsigned)p.v_hi; p.chk[7] = ((long long)p.plan_early << 40) | ((long long)p.R << 20) | gridDim.x; p.chk[0] = 1;                                               \
+      __threadfence_system();                                                                                    \
+      __trap();                                                                                                  \
+    }                                                                                                            \
+  } while (0)
+#else
+#define MOT_ASSERT(cond, what, a, b) do { } while (0)
+#endif
 // PDL: let the next kernel in the stream start launching / block until every predecessor grid has completed and its
 // memory is visible.  Both are no-ops when the kernel was launched without the PDL attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Global loads that STAY BELOW griddepcontrol.wait.  The __ldg() intrinsic is an invariant load to the compiler: it may
+// hoist it above an `asm volatile(... ::: "memory")`, i.e. above pdl_wait(), and the kernel then reads what its
+// predecessor in the programmatic-launch chain has not written yet (seen in round 2: off[V] of the sort plan read before
+// plan_scan_kernel had stored it, once the launches were dense enough for the overlap to happen).  volatile asm
+// statements keep their order among themselves, so these do not move across pdl_wait().
+__device__ __forceinline__ int ld_g(const int* p) {
+  int v;
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ long long ld_g(const long long* p) {
+  long long v;
+  asm volatile("ld.global.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_g(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ short ld_g(const short* p) {
+  short v;
+  asm volatile("ld.global.s16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_g(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.global.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

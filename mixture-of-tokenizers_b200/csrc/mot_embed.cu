@@ -8,11 +8,11 @@ namespace mot {
 // ======================================================================================
 // Backward plan: group positions by token id (counting sort over the vocabulary)
 // ======================================================================================
-__global__ void plan_hist_kernel(const int32_t* __restrict__ tok, long long N, int V, int* __restrict__ cnt) {
+__global__ void plan_hist_kernel(const int32_t* tok, long long N, int V, int* cnt) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&cnt[clampi(tok[i], V - 1)], 1);
+    atomicAdd(&cnt[clampi(ld_g(tok + i), V - 1)], 1);
 }
 
 // Exclusive scan of the histogram -> segment offsets.  One 256-thread CTA per 1024-entry tile (four entries per
@@ -78,7 +78,7 @@ __global__ void plan_fill_kernel(EmbedParams p) {
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.N) {
-    const int v = clampi(p.tok[i], p.V - 1);
+    const int v = clampi(ld_g(p.tok + i), p.V - 1);
     const int slot = atomicSub(&p.cnt[v], 1) - 1;
     const int at = p.off[v] + slot;
     p.order[at] = (int)i;
@@ -86,7 +86,7 @@ __global__ void plan_fill_kernel(EmbedParams p) {
   }
 }
 
-__global__ void mot_lam_store_kernel(float* __restrict__ acc, float* __restrict__ g_lam) {
+__global__ void mot_lam_store_kernel(float* acc, float* g_lam) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x < 2) {
@@ -261,6 +261,8 @@ static void bind_ws(EmbedParams& p, const WsLayout& w, void* ws) {
   p.order = reinterpret_cast<int*>(b + w.order);
   p.stok = reinterpret_cast<int*>(b + w.stok);
   p.partial = reinterpret_cast<float*>(b + w.partial);
+  p.chk = chk_record();
+  p.n_slots = (int)((w.zero_end - w.partial) / ((size_t)(p.Dt > 0 ? p.Dt : 8) * 4));
 }
 
 static int run_plan(const EmbedParams& p, cudaStream_t s) {

@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   // ---- this launch's part of the stream: the entries of the vocabulary rows [v_lo, v_hi), i.e. [a0, a1) (the whole
   //      stream unless the backward runs as slabs of the data-parallel pipeline).  Chunks keep their GLOBAL numbering
   //      (chunk c = entries [c R, (c+1) R)), clipped to [a0, a1): a slab starts and ends on a row boundary.
-  const int a0 = __ldg(p.off + p.v_lo), a1 = __ldg(p.off + p.v_hi);
+  const int a0 = ld_g(p.off + p.v_lo), a1 = ld_g(p.off + p.v_hi);
   const int c_lo = a0 / R, c_hi = (a1 + R - 1) / R;
+  MOT_ASSERT(a0 >= 0 && a0 <= a1 && a1 <= Ni, "stream range", a0, a1);
+  MOT_ASSERT(p.v_lo >= 0 && p.v_lo <= p.v_hi && p.v_hi <= p.V, "row range", p.v_lo, p.v_hi);
 
   // ---- the warp's share: chunks c_lo + gw, c_lo + gw + W, ... walked in batches of <= 32 entries ----
   int nx_chunk = c_lo + gw, nx_a = max(nx_chunk * R, a0);  // the next batch to load
@@ -130,18 +132,21 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
     const int a = nx_a, left = c_end - a;
     b.a = a;
     b.cnt = left < 32 ? left : 32;
+    MOT_ASSERT(a >= a0 && a + b.cnt <= a1 && b.cnt >= 0, "batch range", a, b.cnt);
     if (lane < b.cnt) {
-      b.pos = __ldg(p.order + a + lane);
-      b.v = __ldg(p.stok + a + lane);
-      if (with_r) b.r = __ldg(p.rstd + b.pos);
+      b.pos = ld_g(p.order + a + lane);
+      b.v = ld_g(p.stok + a + lane);
+      MOT_ASSERT(b.pos >= 0 && b.pos < Ni, "position", b.pos, a + lane);
+      MOT_ASSERT(b.v >= p.v_lo && b.v < p.v_hi, "token row", b.v, a + lane);
+      if (with_r) b.r = ld_g(p.rstd + b.pos);
     }
     if (a == c0) {
       b.flags |= 1;
-      if (a > 0) b.v_prev = __ldg(p.stok + a - 1);
+      if (a > 0) b.v_prev = ld_g(p.stok + a - 1);
     }
     if (left <= 32) {
       b.flags |= 2;
-      if (c_end < Ni) b.v_next = __ldg(p.stok + c_end);
+      if (c_end < Ni) b.v_next = ld_g(p.stok + c_end);
       nx_chunk += W;
       nx_a = nx_chunk < c_hi ? max(nx_chunk * R, a0) : 0;
     } else {
@@ -153,8 +158,8 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   load_next(B, !p.plan_early);
   if (p.plan_early) {
     pdl_wait();
-    if (lane < A.cnt) A.r = __ldg(p.rstd + A.pos);
-    if (lane < B.cnt) B.r = __ldg(p.rstd + B.pos);
+    if (lane < A.cnt) A.r = ld_g(p.rstd + A.pos);
+    if (lane < B.cnt) B.r = ld_g(p.rstd + B.pos);
   }
   MOT_STAMP(p.trace, gw, 1);
   MOT_STAMP(p.trace, gw, 2);
@@ -226,12 +231,14 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   auto flush = [&](bool partial_row) {
     if (!partial_row) {
 #ifndef MOT_X_SUM_NO_FLUSH
+      MOT_ASSERT(cur_v >= p.v_lo && cur_v < p.v_hi, "flush row", cur_v, p.v_hi);
       T* grow = G + (size_t)(unsigned)cur_v * (unsigned)p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it) V::stg(grow + (it * 32 + lane) * CW, Du[it]);
 #endif
     } else {
-      const int c_first = __ldg(p.off + cur_v) / R;
+      const int c_first = ld_g(p.off + cur_v) / R;
+      MOT_ASSERT(c_first >= 0 && c_first < p.n_slots, "partial slot", c_first, p.n_slots);
       float* prow = p.partial + (size_t)(unsigned)c_first * (unsigned)p.Dt;
 #pragma unroll
       for (int it = 0; it < CPL; ++it)
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
           dz[e] = r * g[it][e] - c * o[it][e];
           Du[it][e] += dz[e];
         }
+        MOT_ASSERT(id >= 0 && id < p.Vb, "byte id", id, p.Vb);
         gmem_add4(reinterpret_cast<float*>(accp + ((unsigned)id * bd4 + boff4[it])), dz);
       }
 #endif
@@ -372,12 +380,13 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
     while (nb < n_blocks) {
       const int vb = p.v_lo + (nb << 5);
       const int v = vb + lane;
-      const bool empty = v < p.v_hi && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
+      const bool empty = v < p.v_hi && (ld_g(p.off + v + 1) - ld_g(p.off + v)) == 0;
       nb = grab();  // the next block's ticket travels while this block is written
       unsigned m = __ballot_sync(kFull, empty);
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
+        MOT_ASSERT(vb + j >= p.v_lo && vb + j < p.v_hi, "zero row", vb + j, p.v_hi);
         T* row = G + (size_t)(unsigned)(vb + j) * (unsigned)p.Dt;
 #pragma unroll
         for (int it = 0; it < CPL; ++it) V::stg(row + (it * 32 + lane) * CW, zero);

@@ -79,6 +79,8 @@ struct EmbedParams {
                    //    before griddepcontrol.wait
   float eps;
   long long* trace;  // MOT_TRACE builds: per-warp time stamps (nullptr: off)
+  long long* chk;    // MOT_CHECK builds: violation record
+  int n_slots;       // fp32 slots of `partial` (MOT_CHECK builds verify every slot index against it)
 };
 
 struct ChunkMap {
@@ -145,15 +147,15 @@ __device__ __forceinline__ int fetch_id(const EmbedParams& p, long long pos, int
       tokpos = row * p.T + f / p.bpt;
       k = (int)(f % p.bpt);
     }
-    const int tv = clampi(__ldg(p.tok + tokpos), p.V - 1);
+    const int tv = clampi(ld_g(p.tok + tokpos), p.V - 1);
     const size_t e = (size_t)tv * p.bpt + k;
-    if (p.ttb_dtype == MOT_TTB_I16) id = __ldg(reinterpret_cast<const short*>(p.ttb) + e);
-    else if (p.ttb_dtype == MOT_TTB_F32) id = (int)__ldg(reinterpret_cast<const float*>(p.ttb) + e);
+    if (p.ttb_dtype == MOT_TTB_I16) id = ld_g(reinterpret_cast<const short*>(p.ttb) + e);
+    else if (p.ttb_dtype == MOT_TTB_F32) id = (int)ld_g(reinterpret_cast<const float*>(p.ttb) + e);
     else id = (int)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.ttb)[e]);
   } else {
     const long long idx = (p.flags & MOT_F_SLOT_MAJOR) ? (long long)slot * p.N + pos : pos * p.bpt + slot;
-    id = (p.flags & MOT_F_IDS_I64) ? (int)__ldg(reinterpret_cast<const long long*>(p.ids) + idx)
-                                   : __ldg(reinterpret_cast<const int*>(p.ids) + idx);
+    id = (p.flags & MOT_F_IDS_I64) ? (int)ld_g(reinterpret_cast<const long long*>(p.ids) + idx)
+                                   : ld_g(reinterpret_cast<const int*>(p.ids) + idx);
   }
   return id;
 }
@@ -177,7 +179,7 @@ __device__ __forceinline__ IdSrc make_id_src(const EmbedParams& p, int slot) {
 __device__ __forceinline__ int load_raw_id(const EmbedParams& p, const IdSrc& s, int pos, int slot) {
   if (s.kind == 2) return fetch_id(p, pos, slot);
   const char* a = s.base + (unsigned long long)(unsigned)pos * s.pos_stride;  // one 32 x 32 -> 64 multiply-add
-  return s.kind == 1 ? (int)__ldg(reinterpret_cast<const long long*>(a)) : __ldg(reinterpret_cast<const int*>(a));
+  return s.kind == 1 ? (int)ld_g(reinterpret_cast<const long long*>(a)) : ld_g(reinterpret_cast<const int*>(a));
 }
 
 // Compile-time specialisation of the variant flags.  MODE 0: everything decided at run time (all variants);
@@ -373,11 +375,11 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
   int tok_ahead = 0;  // lane 0: raw token id of position i + D
   if (has_tok && lane == 0) {
     for (int i = 0; i < D && i < n_i; ++i) {
-      const int tv = clampi(__ldg(p.tok + gw + i * stride), p.V - 1);
+      const int tv = clampi(ld_g(p.tok + gw + i * stride), p.V - 1);
       mbar_expect_tx(bars + i, row_bytes);
       bulk_g2s(ring + (size_t)i * L.stage_bytes, E_tok + mul_u32(tv, p.Dt), row_bytes, bars + i);
     }
-    if (D < n_i) tok_ahead = __ldg(p.tok + gw + D * stride);  // raw; clamped where it is used
+    if (D < n_i) tok_ahead = ld_g(p.tok + gw + D * stride);  // raw; clamped where it is used
   }
   MOT_STAMP(p.trace, gw, 2);
   if (has_bytes) stage_byte_table<T>(p, tab, rs, &tab_bar, C::byte_scale(p), /*issued=*/true);
@@ -389,8 +391,8 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
 
   float lam_t = 1.f, lam_b = 1.f;
   if (C::has_lam(p)) {
-    lam_t = __ldg(p.lam);
-    lam_b = __ldg(p.lam + 1);
+    lam_t = ld_g(p.lam);
+    lam_b = ld_g(p.lam + 1);
   }
   if (C::mean(p)) lam_b /= (float)p.bpt;
   T* out = reinterpret_cast<T*>(p.out);
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(NT, 1) mot_fwd_kernel(const EmbedParams p) {
     if (has_tok && lane == 0 && i + D < n_i) {
       mbar_expect_tx(bars + s, row_bytes);
       bulk_g2s(ring + (size_t)s * L.stage_bytes, E_tok + mul_u32(clampi(tok_ahead, p.V - 1), p.Dt), row_bytes, bars + s);
-      if (i + D + 1 < n_i) tok_ahead = __ldg(p.tok + pos + (D + 1) * stride);
+      if (i + D + 1 < n_i) tok_ahead = ld_g(p.tok + pos + (D + 1) * stride);
     }
     if (++s == D) {
       s = 0;
@@ -653,8 +655,8 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
     b.sub = nx_sub;
     if (lane < b.cnt) {
       if (has_tok) {
-        b.pos = __ldg(p.order + a + lane);
-        b.v = __ldg(p.stok + a + lane);
+        b.pos = ld_g(p.order + a + lane);
+        b.v = ld_g(p.stok + a + lane);
       } else {
         b.pos = a + lane;  // bytes-only: no token table, the stream is the position order
         b.v = 0;
@@ -710,8 +712,8 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
   const bool has_lam = C::has_lam(p);
   float lam_t = 1.f, lam_b = 1.f;
   if (has_lam) {
-    lam_t = __ldg(p.lam);
-    lam_b = __ldg(p.lam + 1);
+    lam_t = ld_g(p.lam);
+    lam_b = ld_g(p.lam + 1);
   }
   const float inv_pool = C::mean(p) ? 1.f / (float)p.bpt : 1.f;
   const float lam_b_eff = lam_b * inv_pool;
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
     const float zero[CW] = {0.f, 0.f, 0.f, 0.f};
     for (int vb = gw * 32; vb < p.V; vb += W * 32) {
       const int v = vb + lane;
-      const bool empty = v < p.V && (__ldg(p.off + v + 1) - __ldg(p.off + v)) == 0;
+      const bool empty = v < p.V && (ld_g(p.off + v + 1) - ld_g(p.off + v)) == 0;
       unsigned m = __ballot_sync(0xffffffffu, empty);
       while (m) {
         const int j = __ffs(m) - 1;
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
       // the row continues in another chunk: add this segment into the fp32 slot of the row's FIRST chunk (a chunk is
       // the first chunk of at most one such row: its last one).  Hot rows spread over many chunks meet there through
       // the L2 atomic units; the finalize kernel reads the one slot, writes the row and zeroes the slot again.
-      const int c_first = __ldg(p.off + cur_v) / p.R;
+      const int c_first = ld_g(p.off + cur_v) / p.R;
       float* prow = p.partial + mul_u32(c_first, p.Dt);
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
@@ -778,7 +780,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
     const int a = chunk * p.R + A.sub * 32;
     const bool chunk_first = A.sub == 0, chunk_last = a + 32 >= min(chunk * p.R + p.R, Ni);
     int v_before = -1;
-    if (has_tok && chunk_first && a > 0) v_before = __ldg(p.stok + a - 1);
+    if (has_tok && chunk_first && a > 0) v_before = ld_g(p.stok + a - 1);
     const int pos_first = __shfl_sync(0xffffffffu, A.pos, 0);  // warp collective: outside lane-dependent branches
     int id_next = id_lane ? load_raw_id(p, idsrc, pos_first, lane) : 0;
     for (int k = 0; k < A.cnt; ++k) {
@@ -953,7 +955,7 @@ __global__ void __launch_bounds__((bwd_threads<CPL, MODE>()), 1) mot_bwd_kernel(
     // at the end of a chunk the open row segment is flushed
     if (chunk_last && has_tok && cur_v >= 0) {
       const int b_end = chunk * p.R + p.R;
-      const bool trail = b_end < Ni && __ldg(p.stok + b_end) == cur_v;
+      const bool trail = b_end < Ni && ld_g(p.stok + b_end) == cur_v;
       flush(trail);
       cur_v = -1;
       seg_lead = false;
@@ -1000,7 +1002,7 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
   const bool has_bytes = p.combine != MOT_TOK_ONLY;
   const bool has_lam = (p.flags & MOT_F_HAS_LAMBDAS) != 0;
   float lam_t = 1.f;
-  if (has_lam) lam_t = __ldg(p.lam);
+  if (has_lam) lam_t = ld_g(p.lam);
   float dlam_t = 0.f;
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.lam_acc != nullptr)
     reinterpret_cast<int*>(p.lam_acc)[2] = 0;  // zero-fill work counter of the saved-output backward (self-cleaning)
@@ -1008,15 +1010,19 @@ __global__ void __launch_bounds__(256) mot_bwd_finalize_kernel(const EmbedParams
     const bool tok_norm = (p.flags & MOT_F_TOK_NORM) != 0;
     // chunk boundaries strictly inside this launch's part of the stream [off[v_lo], off[v_hi]) (the whole stream unless
     // the backward runs as vocabulary slabs): a slab starts and ends on a row boundary, so no row crosses it
-    const long long a0 = __ldg(p.off + p.v_lo), a1 = __ldg(p.off + p.v_hi);
+    const long long a0 = ld_g(p.off + p.v_lo), a1 = ld_g(p.off + p.v_hi);
     const long long c_lo = a0 / p.R, c_hi = (a1 + p.R - 1) / p.R;
     const T* E_tok = reinterpret_cast<const T*>(p.E_tok);
     T* G = reinterpret_cast<T*>(p.gE_tok);
+    MOT_ASSERT(a0 >= 0 && a0 <= a1 && a1 <= p.N, "finalize stream range", a0, a1);
     for (long long c0 = c_lo + gw; c0 + 1 < c_hi; c0 += W) {
+      MOT_ASSERT(c0 >= 0 && c0 < p.n_slots, "finalize slot", c0, p.n_slots);
       const long long bnd = (c0 + 1) * (long long)p.R;  // first stream entry of chunk c0 + 1
-      const int v = __ldg(p.stok + bnd - 1);
-      if (__ldg(p.stok + bnd) != v) continue;                  // no row crosses this boundary
-      if (__ldg(p.off + v) < c0 * (long long)p.R) continue;    // the row started in an earlier chunk: not ours
+      MOT_ASSERT(bnd > 0 && bnd < p.N, "finalize boundary", bnd, p.N);
+      const int v = ld_g(p.stok + bnd - 1);
+      MOT_ASSERT(v >= 0 && v < p.V, "finalize token", v, p.V);
+      if (ld_g(p.stok + bnd) != v) continue;                  // no row crosses this boundary
+      if (ld_g(p.off + v) < c0 * (long long)p.R) continue;    // the row started in an earlier chunk: not ours
       float* prow = p.partial + (size_t)c0 * p.Dt;             // all segments of the row were added here
       const T* trow = E_tok + (size_t)v * p.Dt;
       float dot = 0.f, ss = 0.f;

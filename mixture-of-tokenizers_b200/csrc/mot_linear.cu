@@ -263,7 +263,7 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (j < nvalid) {
                 float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? __ldg(p.bias + col + j + e) : 0.f);
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? ld_g(p.bias + col + j + e) : 0.f);
                 Vec<__nv_bfloat16, 8>::stg(dst + j, f);
               }
             }
@@ -274,7 +274,7 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (j < nvalid) {
                 float f[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) f[e] = __uint_as_float(v[j + e]) + ((EPI == EPI_STORE_F32 && p.bias) ? __ldg(p.bias + col + j + e) : 0.f);
+                for (int e = 0; e < 4; ++e) f[e] = __uint_as_float(v[j + e]) + ((EPI == EPI_STORE_F32 && p.bias) ? ld_g(p.bias + col + j + e) : 0.f);
                 if (EPI == EPI_RED_F32) atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(f[0], f[1], f[2], f[3]));
                 else Vec<float, 4>::stg(dst + j, f);
               }
@@ -305,7 +305,7 @@ mot_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // bf16 / fp32 rows, one warp per row, 16-byte accesses.  HBM bound: 2 * D * e bytes per row forward, 3 * D * e backward.
 // ======================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ y, T* __restrict__ out, long long n, int D, float eps) {
+__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* y, T* out, long long n, int D, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = lane_id();
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const T* __restrict__ 
 
 // dy = rs * g - y * rs^3 * mean(g . y)
 template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ y, const T* __restrict__ g, T* __restrict__ dy, long long n,
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* y, const T* g, T* dy, long long n,
                                                           int D, float eps) {
   pdl_launch_dependents();
   pdl_wait();
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const T* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n8) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 // dst[c][r] = src[r][c] for fp32 (32 x 32 tiles through shared memory).  Only the fp32 (TF32) backward uses it: the
 // hardware's MN-major operand layout for 32-bit elements is a different swizzle atom than the 16-bit one this kernel
 // stages with TMA, so the two small fp32 backward GEMMs (mathblations: 11 K tokens) run on transposed copies instead.
-__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C, long long ld_dst) {
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* src, float* dst, int R, int C, long long ld_dst) {
   __shared__ float tile[32][33];
   pdl_launch_dependents();
   pdl_wait();

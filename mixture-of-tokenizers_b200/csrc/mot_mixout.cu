@@ -9,8 +9,8 @@
 namespace mot {
 
 template <typename T>
-__global__ void __launch_bounds__(256) mixout_copy_fwd_kernel(const T* __restrict__ x, long long n_pieces, int pieces_per_row, int bpt,
-                                                             T* __restrict__ y) {
+__global__ void __launch_bounds__(256) mixout_copy_fwd_kernel(const T* x, long long n_pieces, int pieces_per_row, int bpt,
+                                                             T* y) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int E = 16 / sizeof(T);
@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(256) mixout_copy_fwd_kernel(const T* __restric
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) mixout_copy_bwd_kernel(const T* __restrict__ gy, long long n_pieces, int pieces_per_row, int bpt,
-                                                             T* __restrict__ gx) {
+__global__ void __launch_bounds__(256) mixout_copy_bwd_kernel(const T* gy, long long n_pieces, int pieces_per_row, int bpt,
+                                                             T* gx) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int E = 16 / sizeof(T);

@@ -48,7 +48,7 @@ __device__ __forceinline__ void pair_stage_table(const PairParams& p, T* tab, ui
 }
 
 __device__ __forceinline__ int pair_load_id(const void* ids, int i64, long long idx, int hi) {
-  const int v = i64 ? (int)__ldg(reinterpret_cast<const long long*>(ids) + idx) : __ldg(reinterpret_cast<const int*>(ids) + idx);
+  const int v = i64 ? (int)ld_g(reinterpret_cast<const long long*>(ids) + idx) : ld_g(reinterpret_cast<const int*>(ids) + idx);
   return clampi(v, hi);
 }
 

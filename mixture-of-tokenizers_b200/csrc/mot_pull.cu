@@ -33,7 +33,7 @@ struct PullParams {
 
 template <typename IdT>
 __device__ __forceinline__ int ld_id(const PullParams& p, long long tok_phys, int slot_phys) {
-  return (int)__ldg(reinterpret_cast<const IdT*>(p.in) + tok_phys * p.bpt + slot_phys);
+  return (int)ld_g(reinterpret_cast<const IdT*>(p.in) + tok_phys * p.bpt + slot_phys);
 }
 // logical token -> physical token (reversed inside its row for pull_from_right)
 __device__ __forceinline__ long long phys_tok(const PullParams& p, long long L) {

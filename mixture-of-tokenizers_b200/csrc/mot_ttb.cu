@@ -10,8 +10,8 @@
 namespace mot {
 
 template <int TTB, typename OutT>
-__global__ void __launch_bounds__(256) ttb_expand_kernel(const int32_t* __restrict__ tok, long long n, const void* __restrict__ ttb,
-                                                        int V, int bpt, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256) ttb_expand_kernel(const int32_t* tok, long long n, const void* ttb,
+                                                        int V, int bpt, OutT* out) {
   const long long total = n * bpt;
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (TTB == MOT_TTB_I16 && (bpt & 3) == 0) {
@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(256) ttb_expand_kernel(const int32_t* __restri
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
       const long long t = g / gpt;
       const int k = (int)(g - t * gpt);
-      const int tv = min(max(__ldg(tok + t), 0), V - 1);
-      const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const short*>(ttb) + (size_t)tv * bpt) + k);
+      const int tv = min(max(ld_g(tok + t), 0), V - 1);
+      const uint2 r = ld_g(reinterpret_cast<const uint2*>(reinterpret_cast<const short*>(ttb) + (size_t)tv * bpt) + k);
       const OutT a = (OutT)(short)(r.x & 0xffffu), b = (OutT)(short)(r.x >> 16), c = (OutT)(short)(r.y & 0xffffu),
                  d = (OutT)(short)(r.y >> 16);
       OutT* o = out + (g << 2);
@@ -33,11 +33,11 @@ __global__ void __launch_bounds__(256) ttb_expand_kernel(const int32_t* __restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long t = i / bpt;
     const int k = (int)(i - t * bpt);
-    const int tv = min(max(__ldg(tok + t), 0), V - 1);
+    const int tv = min(max(ld_g(tok + t), 0), V - 1);
     const size_t e = (size_t)tv * bpt + k;
     long long id;
-    if (TTB == MOT_TTB_I16) id = __ldg(reinterpret_cast<const short*>(ttb) + e);
-    else if (TTB == MOT_TTB_F32) id = (long long)__ldg(reinterpret_cast<const float*>(ttb) + e);  // trunc, like .to(int64)
+    if (TTB == MOT_TTB_I16) id = ld_g(reinterpret_cast<const short*>(ttb) + e);
+    else if (TTB == MOT_TTB_F32) id = (long long)ld_g(reinterpret_cast<const float*>(ttb) + e);  // trunc, like .to(int64)
     else id = (long long)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ttb)[e]);
     out[i] = (OutT)id;
   }
@@ -62,8 +62,8 @@ static int launch_expand(const int32_t* tok, long long n, const void* ttb, int V
 // becomes its decimal digits right-aligned in dpt slots padded with 13; the operator / equals / pad tokens become
 // 10 / 11 / 12 in the last slot.
 template <typename TokT, typename OutT>
-__global__ void __launch_bounds__(256) tokens_to_digits_kernel(const TokT* __restrict__ tok, long long n, int dpt, long long op_token,
-                                                              long long eq_token, long long pad_token, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256) tokens_to_digits_kernel(const TokT* tok, long long n, int dpt, long long op_token,
+                                                              long long eq_token, long long pad_token, OutT* out) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) tokens_to_digits_kernel(const TokT* __res
 // ids every kernel of the path takes, on the device, so that the host -> device copy moves 2 bytes per token instead of
 // the 4 of the reference's host-side `.to(torch.int32)` (spt/train_gpt.py:646).  8 tokens per thread: one 16-byte load,
 // two 16-byte stores; HBM bound at 6 bytes per token.
-__global__ void __launch_bounds__(256) tokens_widen_u16_kernel(const unsigned short* __restrict__ in, long long n, int* __restrict__ out) {
+__global__ void __launch_bounds__(256) tokens_widen_u16_kernel(const unsigned short* in, long long n, int* out) {
   pdl_launch_dependents();
   pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(256) tokens_widen_u16_kernel(const unsigned sh
 // string is the end-of-text marker becomes bpt copies of `eot_byte` (:20-22).  The strings arrive as one flat id
 // stream `chars` with offsets `offs` [n_rows + 1] (a negative length marks an end-of-text row).  One thread per table
 // entry: out[v, k] is either a pad or ONE gathered id, so all stores are coalesced 2-byte writes of consecutive k.
-__global__ void __launch_bounds__(256) ttb_build_kernel(const short* __restrict__ chars, const int* __restrict__ offs,
-                                                       const unsigned char* __restrict__ is_eot, int n_rows, int bpt, int pad_left,
-                                                       int pad_byte, int eot_byte, short* __restrict__ out) {
+__global__ void __launch_bounds__(256) ttb_build_kernel(const short* chars, const int* offs,
+                                                       const unsigned char* is_eot, int n_rows, int bpt, int pad_left,
+                                                       int pad_byte, int eot_byte, short* out) {
   const long long total = (long long)n_rows * bpt;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i / bpt), k = (int)(i - (long long)v * bpt);
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(256) ttb_build_kernel(const short* __restrict_
     if (is_eot != nullptr && is_eot[v]) {
       id = eot_byte;
     } else {
-      const int a = __ldg(offs + v), len = min(__ldg(offs + v + 1) - a, bpt);  // keeps the FIRST bpt characters
+      const int a = ld_g(offs + v), len = min(ld_g(offs + v + 1) - a, bpt);  // keeps the FIRST bpt characters
       const int j = pad_left ? k - (bpt - len) : k;                            // index into the kept characters
-      if (j >= 0 && j < len) id = __ldg(chars + a + j);
+      if (j >= 0 && j < len) id = ld_g(chars + a + j);
     }
     out[i] = (short)id;
   }
@@ -131,12 +131,12 @@ __global__ void __launch_bounds__(256) ttb_build_kernel(const short* __restrict_
 // are the same strings under another (bpt, pad_position), spt/train_gpt.py:665-672).  A row's characters are its non-pad
 // entries in order; rows that are all `eot_byte` stay all `eot_byte`.  One warp per row (bpt <= 32): ballot of the
 // non-pad lanes gives every character its rank, i.e. its place in the re-padded row.
-__global__ void __launch_bounds__(256) ttb_repad_kernel(const short* __restrict__ in, int n_rows, int bpt_in, int bpt_out, int pad_left,
-                                                       int pad_byte, int eot_byte, short* __restrict__ out) {
+__global__ void __launch_bounds__(256) ttb_repad_kernel(const short* in, int n_rows, int bpt_in, int bpt_out, int pad_left,
+                                                       int pad_byte, int eot_byte, short* out) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_rows; v += warps) {
-    const int id = lane < bpt_in ? (int)__ldg(in + (size_t)v * bpt_in + lane) : pad_byte;
+    const int id = lane < bpt_in ? (int)ld_g(in + (size_t)v * bpt_in + lane) : pad_byte;
     const unsigned live = __ballot_sync(0xffffffffu, lane < bpt_in && id != pad_byte);
     const unsigned eot = __ballot_sync(0xffffffffu, lane >= bpt_in || id == eot_byte);
     short* o = out + (size_t)v * bpt_out;

@@ -7,7 +7,7 @@
 
 namespace mot {
 
-__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* in, long long n, __nv_bfloat16* out) {
   pdl_launch_dependents();
   pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 // One CTA owns 64 columns (a lane two adjacent ones: 128-byte / 256-byte warp rows), its 32 warps walk the rows with
 // stride 32 and meet in shared memory in warp order: the summation order is fixed by the shape alone.
 template <typename T>
-__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, long long n_rows, int dim, float* __restrict__ out) {
+__global__ void __launch_bounds__(1024) colsum_kernel(const T* x, long long n_rows, int dim, float* out) {
   __shared__ float part[32][64];
   pdl_launch_dependents();
   pdl_wait();

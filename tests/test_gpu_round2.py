@@ -215,8 +215,13 @@ def test_widest_reference_concat_operand_k3072():
 def test_every_module_captures_into_cuda_graphs(kind):
     """torch.cuda.make_graphed_callables on each module family: the forward rejoins the side stream
     inside the capture; a replayed step reproduces the eager gradients."""
+    import gc
     import mot_b200
     d = dev()
+    # objects of earlier tests (graphs with private pools, tensors last used on a side stream) must not be finalised in the
+    # middle of this test's capture: the caching allocator would query their events, which invalidates a global-mode capture
+    gc.collect()
+    torch.cuda.synchronize()
     torch.manual_seed(7)
     V, N, bpt = 600, 256, 16
     tok = torch.randint(0, V, (N,), device=d, dtype=torch.int32)
@@ -313,7 +318,7 @@ def test_util_kernels_cast_and_colsum():
 
 
 # ------------------------------------------------------------------------------------------- vocabulary slabs (dp pipeline)
-@pytest.mark.parametrize("N,V,n_slabs,zipf,reserve", [(49152, 50257, 4, False, 8), (20000, 3000, 3, True, 16), (700, 50257, 8, False, 0),
+@pytest.mark.parametrize("N,V,n_slabs,zipf,reserve", [(49152, 50257, 4, False, 8), (20000, 6000, 3, True, 16), (700, 50257, 8, False, 0),
                                                       (5, 64, 2, False, 0)])
 def test_backward_as_vocabulary_slabs_equals_one_piece(N, V, n_slabs, zipf, reserve):
     """mot_embed_bwd_slab k = 0..n-1 (what the data-parallel pipeline runs beside the exchange) against mot_embed_bwd_ex
