@@ -458,6 +458,7 @@ def run_ours(args):
                                plan_joined=True)
         ws.clean = True
         if world > 1 and exchange:
+            bucket.mark_rows(desc, ws.buf)      # touched-rows exchange (no-op where the bucket does not offer it)
             bucket.all_reduce_avg()
 
     def step():
@@ -528,7 +529,9 @@ def run_ours(args):
             t_ = torch.tensor([a.elapsed_time(b) / reps], device=dev)
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
             return float(t_.item())
-        ar_ms = timed(bucket.all_reduce_avg, max(10, K // 4))                 # the whole bucket, one exchange
+        ar_ms = timed(bucket.all_reduce_avg, max(10, K // 4))                 # the whole bucket, one (dense) exchange
+        ar_rows_ms = timed(lambda: (bucket.mark_rows(desc, ws.buf), bucket.all_reduce_avg()), max(10, K // 4)) \
+            if bucket.sparse_rows else None                                   # bitmap + touched-rows exchange
         comp_ms = timed(lambda: compute_step(False), max(10, K // 4))         # fwd + bwd (slabs), no exchange
         nccl_buf = bucket.flat.clone()
         nccl_ms = timed(lambda: dist.all_reduce(nccl_buf, op=dist.ReduceOp.AVG), max(10, K // 4))
@@ -543,8 +546,15 @@ def run_ours(args):
         err = float((bucket.flat.float() - want).abs().max() / want.abs().max().clamp_min(1e-30))
         errt = torch.tensor([err], device=dev)
         dist.all_reduce(errt, op=dist.ReduceOp.MAX)
-        dp_info = {"exchange": bucket.algo, "n_slabs": n_slabs, "reserve_sms": bucket.reserve_sms if n_slabs > 1 else 0,
-                   "allreduce_ms": ar_ms, "nccl_allreduce_ms": nccl_ms, "compute_only_ms": comp_ms,
+        union_density = None
+        if bucket.sparse_rows:
+            bm = bucket.bitmap.clone()
+            dist.all_reduce(bm, op=dist.ReduceOp.BOR)
+            bits = bm.view(torch.uint8)
+            union_density = float(sum(int(((bits >> k) & 1).sum()) for k in range(8))) / V_TOK
+        dp_info = {"exchange": bucket.algo + (" (touched rows only)" if bucket.sparse_rows else ""), "rows_union_density": union_density,
+                   "n_slabs": n_slabs, "reserve_sms": bucket.reserve_sms if n_slabs > 1 else 0,
+                   "allreduce_ms": ar_ms, "touched_rows_allreduce_ms": ar_rows_ms, "nccl_allreduce_ms": nccl_ms, "compute_only_ms": comp_ms,
                    "bucket_mb": bucket.flat.numel() * esz / 1e6,
                    "allreduce_algbw_gbs": bucket.flat.numel() * esz / (ar_ms * 1e-3) / 1e9,
                    "exposed_exchange_ms": ms_step - comp_ms,
@@ -795,13 +805,14 @@ def run_proj(args):
 
     def scatter_dA():
         if pair:
-            ops.embed_backward_out(desc, tok, None, None, E_tok, None, None, A, gE_tok, None, None, ws.buf,
+            ops.embed_backward_out(desc, tok, None, None, E_tok, None, None, dA, gE_tok, None, None, ws.buf,
                                    plan_ready=True, ws_clean=True)
-            ops.byte_pair_backward_out(ids, ids2, bpt, E_byte, A, Dt, gE_byte)
+            ops.byte_pair_backward_out(ids, ids2, bpt, E_byte, dA, Dt, gE_byte)
         else:
-            ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, A, gE_tok, gE_byte, None, ws.buf,
+            ops.embed_backward_out(desc, tok, ids, None, E_tok, E_byte, None, dA, gE_tok, gE_byte, None, ws.buf,
                                    plan_ready=True, ws_clean=True)
     A = torch.empty(N, K, dtype=dt, device=dev)
+    dA = torch.empty(N, K, dtype=dt, device=dev)
     Y, out, dY = (torch.empty(N, Do, dtype=dt, device=dev) for _ in range(3))
     dW32 = torch.empty(Do, K, dtype=torch.float32, device=dev)
     bucket = dp.GradBucket([torch.nn.Parameter(E_tok, requires_grad=False), torch.nn.Parameter(E_byte, requires_grad=False),
@@ -824,9 +835,11 @@ def run_proj(args):
         ops.rmsnorm_forward_out(Y, out)
         # backward: norm bwd -> dW, dX on the tensor cores -> fused scatter into the dense table gradients
         ops.rmsnorm_backward_out(Y, gout, dY)
-        gather_A()                                                                # operand gathered again, not kept
+        # the [N, K] operand of the forward is kept (like mot_b200.mot_embed_proj; MOT_PROJ_REGATHER=1 gathers it again)
+        if os.environ.get("MOT_PROJ_REGATHER"):
+            gather_A()
         timed("dw", lambda: ops.linear_bwd_weight_out(dY, A, dW32, gW), record)
-        timed("dx", lambda: ops.linear_bwd_input_out(dY, W, A), record)          # dX overwrites the operand buffer
+        timed("dx", lambda: ops.linear_bwd_input_out(dY, W, dA), record)
         ops.embed_plan_join(ws, dev)
         scatter_dA()
         ws.clean = True

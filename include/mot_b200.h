@@ -274,6 +274,17 @@ enum { MOT_DP_NVLS = 0, MOT_DP_P2P = 1 };
 int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
                     int32_t rank, int32_t world, int64_t byte_offset, int64_t n_bytes, int32_t dtype, uint32_t epoch,
                     int32_t last, int32_t algo, void* stream);
+/* Touched-rows exchange.  A vocabulary row that no rank gathered is zero in every copy and needs no exchange.
+ * mot_embed_touched_rows writes this rank's bitmap (bit v of word v/32: the batch of the planned workspace contains token
+ * v; ceil(tok_vocab/32) uint32 words) -- call it after the backward, into the bucket's symmetric memory.
+ * mot_dp_exchange_rows ORs the ranks' bitmaps through the fabric and averages only the rows of the union of the table at
+ * [table_byte_offset, + n_rows*row_bytes), then the dense range [dense_byte_offset, + dense_bytes) (the byte table, other
+ * parameters); both barriers: `epoch` grows by 2.  Rows that are zero everywhere stay untouched. */
+int mot_embed_touched_rows(const MotDesc* d, const void* workspace, size_t ws_bytes, uint32_t* bitmap, void* stream);
+int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
+                         int32_t rank, int32_t world, int64_t table_byte_offset, int32_t n_rows, int32_t row_bytes,
+                         int64_t bitmap_byte_offset, int64_t dense_byte_offset, int64_t dense_bytes, int32_t dtype,
+                         uint32_t epoch, int32_t algo, void* stream);
 /* The whole bucket as one NVLS range with both barriers (= mot_dp_exchange(..., 0, n_bytes, ..., last = 1, MOT_DP_NVLS)):
  * `epoch` grows by 2 per call. */
 int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pads_dev, void* work_area, int32_t rank, int32_t world,

@@ -215,6 +215,180 @@ static void launch_p2p(int unroll, dim3 g, dim3 b, cudaStream_t s, char* const* 
     launch_pdl(p2p_allreduce_avg_kernel<BF16, WORLD, 1>, g, b, 0, s, peers, pads, rank, vec_lo, n_vec, epoch, last, work, trace);
 }
 
+
+// ---- touched-rows exchange ------------------------------------------------------------------------------------------
+// The dense token gradient has a row of zeros for every token the rank's batch did not contain, and a row that is zero on
+// EVERY rank needs no exchange at all: it is already correct everywhere.  Each rank publishes a bitmap of the rows its
+// backward gathered (mot_embed_touched_rows, from the sort plan) next to the bucket; the exchange ORs the bitmaps through
+// the same fabric (multimem.ld_reduce.or / peer loads) and moves only the rows of the union.  Uniform synthetic ids at 48K
+// tokens touch 62 % of the vocabulary per rank (union 86 % at 2 ranks, ~100 % from 4 ranks on: no gain there); Zipf /
+// real text touches 20-30 % per rank.  Work unit: 64 rows (two bitmap words), handed out by the tile counter; a warp owns a
+// row, its lanes the row's 16-byte vectors.
+constexpr int kRowsPerTile = 64;
+constexpr int kMaxVecPerLane = 4;   // rows up to 32 x 4 x 16 = 2048 bytes in one trip; wider rows loop
+
+template <bool BF16, bool NVLS, int WORLD>
+__global__ void __launch_bounds__(1024) rows_allreduce_avg_kernel(char* mc, char* const* peers, uint32_t* const* pads, int rank, int world,
+                                                                 long long tab_off, int n_rows, int row_vecs, long long bm_off,
+                                                                 long long dense_vec_lo, long long dense_vecs, uint32_t epoch,
+                                                                 unsigned* work, long long* trace) {
+  pdl_launch_dependents();
+  MOT_STAMP(trace, blockIdx.x, 0);
+  pdl_wait();
+  MOT_STAMP(trace, blockIdx.x, 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) work[(epoch + 1u) & 63u] = work[(epoch + 2u) & 63u] = 0u;
+  work += epoch & 63u;
+  rank_barrier(pads, rank, world, epoch);
+  MOT_STAMP(trace, blockIdx.x, 2);
+  char* P[WORLD];
+  if (!NVLS) {
+#pragma unroll
+    for (int q = 0; q < WORLD; ++q) P[q] = peers[q];
+  }
+  const float inv = 1.f / (float)world;
+  // rows of this rank: a multiple of 32 per rank, so that a bitmap word belongs to one rank
+  const int per = ((n_rows + world - 1) / world + 31) / 32 * 32;
+  const int r_lo = min(per * rank, n_rows), r_hi = min(r_lo + per, n_rows);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ long long tile_s[2];
+  __shared__ uint32_t bits_s[2][kRowsPerTile / 32];
+  auto or_word = [&](int w) -> uint32_t {  // union over the ranks of bitmap word w
+    uint32_t v = 0;
+    if (NVLS) {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b32 %0, [%1];" : "=r"(v) : "l"(mc + bm_off + (long long)w * 4) : "memory");
+    } else {
+#pragma unroll
+      for (int q = 0; q < WORLD; ++q) {
+        uint32_t x;
+        asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(x) : "l"(P[q] + bm_off + (long long)w * 4) : "memory");
+        v |= x;
+      }
+    }
+    return v;
+  };
+  if (threadIdx.x == 0) tile_s[0] = (long long)atomicAdd(work, 1u);
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const long long row0 = (long long)r_lo + tile_s[it & 1] * kRowsPerTile;
+    if (row0 >= r_hi) break;
+    if (threadIdx.x == 0) tile_s[(it + 1) & 1] = (long long)atomicAdd(work, 1u);
+    if (threadIdx.x < kRowsPerTile / 32) bits_s[it & 1][threadIdx.x] = or_word((int)(row0 >> 5) + threadIdx.x);
+    __syncthreads();
+    for (int rr = warp; rr < kRowsPerTile; rr += nw) {
+      const long long row = row0 + rr;
+      if (row >= r_hi) break;
+      if (!((bits_s[it & 1][rr >> 5] >> (rr & 31)) & 1u)) continue;   // zero on every rank: nothing to move
+      const long long v0 = tab_off / 16 + row * row_vecs;
+      for (int j0 = 0; j0 < row_vecs; j0 += 32 * kMaxVecPerLane) {
+        uint32_t r[kMaxVecPerLane][4];
+        if (NVLS) {
+#pragma unroll
+          for (int u = 0; u < kMaxVecPerLane; ++u) {
+            const int j = j0 + u * 32 + lane;
+            if (j < row_vecs) {
+              char* a = mc + (v0 + j) * 16;
+              if (BF16)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(r[u][0]), "=r"(r[u][1]), "=r"(r[u][2]), "=r"(r[u][3]) : "l"(a) : "memory");
+              else
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(r[u][0]), "=r"(r[u][1]), "=r"(r[u][2]), "=r"(r[u][3]) : "l"(a) : "memory");
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kMaxVecPerLane; ++u) {
+            const int j = j0 + u * 32 + lane;
+            if (j < row_vecs) {
+              scale_vec(r[u], inv, BF16);
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + (v0 + j) * 16), "r"(r[u][0]),
+                           "r"(r[u][1]), "r"(r[u][2]), "r"(r[u][3]) : "memory");
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int u = 0; u < kMaxVecPerLane; ++u) {
+            const int j = j0 + u * 32 + lane;
+            if (j < row_vecs) {
+              uint32_t v[WORLD][4];
+#pragma unroll
+              for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + (v0 + j) * 16, v[q]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (BF16) {
+                  float a = 0.f, b = 0.f;
+#pragma unroll
+                  for (int q = 0; q < WORLD; ++q) {
+                    float lo_f, hi_f;
+                    bf16x2_to_f32(v[q][k], lo_f, hi_f);
+                    a += lo_f;
+                    b += hi_f;
+                  }
+                  r[u][k] = f32x2_to_bf16x2(a * inv, b * inv);
+                } else {
+                  float a = 0.f;
+#pragma unroll
+                  for (int q = 0; q < WORLD; ++q) a += __uint_as_float(v[q][k]);
+                  r[u][k] = __float_as_uint(a * inv);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + (v0 + j) * 16, r[u]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // the rest of the bucket (byte table, anything else): dense, this rank's share, a static stride loop (it is small)
+  {
+    const long long dper = (dense_vecs + world - 1) / world;
+    const long long lo = dense_vec_lo + dper * rank, hi = min(lo + dper, dense_vec_lo + dense_vecs);
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+      uint32_t r[4];
+      if (NVLS) {
+        if (BF16)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(mc + i * 16) : "memory");
+        else
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(mc + i * 16) : "memory");
+        scale_vec(r, inv, BF16);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 16), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                     "r"(r[3]) : "memory");
+      } else {
+        uint32_t v[WORLD][4];
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + i * 16, v[q]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (BF16) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) {
+              float lo_f, hi_f;
+              bf16x2_to_f32(v[q][k], lo_f, hi_f);
+              a += lo_f;
+              b += hi_f;
+            }
+            r[k] = f32x2_to_bf16x2(a * inv, b * inv);
+          } else {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < WORLD; ++q) a += __uint_as_float(v[q][k]);
+            r[k] = __float_as_uint(a * inv);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + i * 16, r);
+      }
+    }
+  }
+  MOT_STAMP(trace, blockIdx.x, 3);
+  rank_barrier(pads, rank, world, epoch + 1u);
+  MOT_STAMP(trace, blockIdx.x, 4);
+}
+
 }  // namespace mot
 
 using namespace mot;
@@ -292,4 +466,50 @@ extern "C" int mot_dp_allreduce_avg(void* multicast_ptr, void* const* signal_pad
   if (!multicast_ptr) return MOT_ERR_BAD_ARG;
   return mot_dp_exchange(multicast_ptr, nullptr, signal_pads_dev, work_area, rank, world, 0, n_bytes, dtype, epoch, 1, MOT_DP_NVLS,
                          stream);
+}
+
+extern "C" int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
+                                    int32_t rank, int32_t world, int64_t table_byte_offset, int32_t n_rows, int32_t row_bytes,
+                                    int64_t bitmap_byte_offset, int64_t dense_byte_offset, int64_t dense_bytes, int32_t dtype,
+                                    uint32_t epoch, int32_t algo, void* stream) {
+  if (!signal_pads_dev || !work_area || world < 1 || rank < 0 || rank >= world || n_rows < 0 || row_bytes <= 0 || dense_bytes < 0)
+    return MOT_ERR_BAD_ARG;
+  if (dtype != MOT_BF16 && dtype != MOT_F32) return MOT_ERR_UNSUPPORTED;
+  if (algo == MOT_DP_NVLS && !multicast_ptr) return MOT_ERR_BAD_ARG;
+  if (algo == MOT_DP_P2P && !peer_ptrs_dev) return MOT_ERR_BAD_ARG;
+  if (algo != MOT_DP_NVLS && algo != MOT_DP_P2P) return MOT_ERR_UNSUPPORTED;
+  if (algo == MOT_DP_P2P && world != 2 && world != 4) return MOT_ERR_UNSUPPORTED;
+  if (world > 16) return MOT_ERR_UNSUPPORTED;
+  if ((row_bytes & 15) || (table_byte_offset & 15) || (bitmap_byte_offset & 3) || (dense_byte_offset & 15) || (dense_bytes & 15))
+    return MOT_ERR_MISALIGNED;
+  int sms = 0, optin = 0;
+  if (int rc = device_props(&sms, &optin)) return rc;
+  const char* env_b = getenv("MOT_AR_BLOCKS");
+  long long blocks = env_b ? atoi(env_b) : (algo == MOT_DP_NVLS ? kArMaxBlocksNvls : 16);
+  if (blocks < 1) blocks = 1;
+  if (blocks * world > kPadSlots) blocks = kPadSlots / world;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads_dev);
+  unsigned* work = reinterpret_cast<unsigned*>(work_area);
+  static int trace_seq = 0;
+  long long* trace = g_trace ? g_trace + (3 * 4096 + (size_t)(trace_seq++ % 16) * 64) * 64 : nullptr;
+  char* mc = reinterpret_cast<char*>(multicast_ptr);
+  char* const* peers = reinterpret_cast<char* const*>(peer_ptrs_dev);
+  const dim3 g((unsigned)blocks), b(1024);
+  const int row_vecs = row_bytes / 16;
+  const long long dlo = dense_byte_offset / 16, dn = dense_bytes / 16;
+  const bool bf = dtype == MOT_BF16;
+#define MOT_ROWS_LAUNCH(BF, NV, WD)                                                                                         \
+  launch_pdl(rows_allreduce_avg_kernel<BF, NV, WD>, g, b, 0, s, mc, peers, pads, (int)rank, (int)world, (long long)table_byte_offset, \
+             (int)n_rows, row_vecs, (long long)bitmap_byte_offset, dlo, dn, epoch, work, trace)
+  if (algo == MOT_DP_NVLS) {
+    if (bf) MOT_ROWS_LAUNCH(true, true, 1); else MOT_ROWS_LAUNCH(false, true, 1);
+  } else if (world == 2) {
+    if (bf) MOT_ROWS_LAUNCH(true, false, 2); else MOT_ROWS_LAUNCH(false, false, 2);
+  } else {
+    if (bf) MOT_ROWS_LAUNCH(true, false, 4); else MOT_ROWS_LAUNCH(false, false, 4);
+  }
+#undef MOT_ROWS_LAUNCH
+  count_launch();
+  return check_launch();
 }

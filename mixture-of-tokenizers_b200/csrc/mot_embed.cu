@@ -86,6 +86,21 @@ __global__ void plan_fill_kernel(EmbedParams p) {
   }
 }
 
+// Bitmap of the vocabulary rows this batch gathered (bit v of word v / 32 = off[v+1] > off[v]), for the touched-rows
+// exchange of the data-parallel step (mot_dp_exchange_rows).  One warp per word.
+__global__ void __launch_bounds__(256) plan_rowmap_kernel(const int* off, int V, uint32_t* bitmap) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int words = (V + 31) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words; w += (gridDim.x * blockDim.x) >> 5) {
+    const int v = (w << 5) + lane;
+    const bool hit = v < V && ld_g(off + v + 1) > ld_g(off + v);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) bitmap[w] = m;
+  }
+}
+
 __global__ void mot_lam_store_kernel(float* acc, float* g_lam) {
   pdl_launch_dependents();
   pdl_wait();
@@ -536,4 +551,20 @@ extern "C" int mot_embed_slab_rows(int32_t tok_vocab, int32_t slab, int32_t n_sl
   *row_lo = (int32_t)((long long)tok_vocab * slab / n_slabs);
   *row_hi = (int32_t)((long long)tok_vocab * (slab + 1) / n_slabs);
   return MOT_OK;
+}
+
+extern "C" int mot_embed_touched_rows(const MotDesc* d, const void* workspace, size_t ws_bytes, uint32_t* bitmap, void* stream) {
+  if (int rc = validate(d)) return rc;
+  if (d->combine == MOT_BYTES_ONLY) return MOT_ERR_UNSUPPORTED;
+  if (!workspace || !bitmap) return MOT_ERR_BAD_ARG;
+  EmbedParams p;
+  fill_params(d, p);
+  const WsLayout w = ws_layout(p, d->dp_slabs);
+  if (ws_bytes < w.total) return MOT_ERR_WORKSPACE;
+  bind_ws(p, w, const_cast<void*>(workspace));
+  const int words = (p.V + 31) / 32;
+  launch_pdl(plan_rowmap_kernel, dim3((unsigned)((words + 7) / 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             (const int*)p.off, (int)p.V, bitmap);
+  count_launch();
+  return check_launch();
 }

@@ -88,7 +88,7 @@ class GradBucket:
     from its asynchronous per-parameter all-reduces (runs/7:697-711), inside the path."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None, symmetric="auto",
-                 group=None, n_slabs: Optional[int] = None, reserve_sms: int = 8):
+                 group=None, n_slabs: Optional[int] = None, reserve_sms: int = 8, sparse_rows="auto"):
         """symmetric=True / "auto" (CUDA, initialised process group with more than one rank): allocate the bucket in
         symmetric memory so that the library's own exchange kernels apply; False: ordinary memory, NCCL."""
         self.params: List[torch.nn.Parameter] = list(params)
@@ -111,7 +111,13 @@ class GradBucket:
         self.reserve_sms = int(reserve_sms)
         self._ev = None
         self._pending = False
+        self.sparse_rows = False          # touched-rows exchange of params[0] (a [V, D] table) available
+        self.bitmap = None
+        self._rows_ready = False
         n = (n + align - 1) // align * align
+        # room for the touched-rows bitmap of the first table behind the gradients (same symmetric allocation)
+        words = (self.params[0].shape[0] + 31) // 32 if self.params[0].dim() == 2 else 0
+        extra = (words * 4 + 15) // 16 * 16 // esz
         self.flat = None
         have_group = dist.is_available() and dist.is_initialized()
         world = dist.get_world_size(group) if have_group else 1
@@ -122,12 +128,18 @@ class GradBucket:
             # collective on the same data, not a different code path for the kernels).
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                flat = symm_mem.empty(n, dtype=self.dtype, device=dev)
-                flat.zero_()
-                hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+                full = symm_mem.empty(n + extra, dtype=self.dtype, device=dev)
+                full.zero_()
+                hdl = symm_mem.rendezvous(full, dist.group.WORLD)
                 algo = pick_algo(world, hdl.multicast_ptr != 0)
                 if algo != "nccl":
-                    self.flat, self._symm, self.algo = flat, hdl, algo
+                    self._full = full
+                    self.flat, self._symm, self.algo = full[:n], hdl, algo
+                    want_sparse = sparse_rows if sparse_rows != "auto" else not os.environ.get("MOT_DP_DENSE")
+                    if want_sparse and words > 0 and (algo == "nvls" or world in (2, 4)) and self.params[0].is_contiguous():
+                        self.sparse_rows = True
+                        self.bitmap = full[n:].view(torch.int32)[:words]
+                        self._bitmap_off = n * esz
                     self.n_slabs = max(1, int(os.environ.get("MOT_DP_SLABS", n_slabs if n_slabs is not None
                                                              else default_slabs(world))))
                     self._ev = torch.cuda.Event()
@@ -185,6 +197,36 @@ class GradBucket:
         L.check(rc, "mot_dp_exchange")
         self._epoch = (self._epoch + (2 if last else 1)) & 0xFFFFFFFF
 
+    def mark_rows(self, desc, ws_buf: torch.Tensor) -> None:
+        """Publish the rows of params[0] this rank's batch gathered (from the sort plan in `ws_buf`) for the touched-rows
+        exchange; call after the backward of the step, on its stream.  The next all_reduce_avg() then moves only the rows
+        some rank gathered (rows that are zero everywhere stay as they are)."""
+        if not self.sparse_rows:
+            return
+        from . import _lib as L
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            rc = L.lib().mot_embed_touched_rows(desc, ws_buf.data_ptr(), ws_buf.numel(), self.bitmap.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream)
+        L.check(rc, "mot_embed_touched_rows")
+        self._rows_ready = True
+
+    def _exchange_rows(self, stream: int) -> None:
+        from . import _lib as L
+        h = self._symm
+        esz = self.flat.element_size()
+        V, D = self.params[0].shape
+        dense_lo = self.offsets[1] if len(self.offsets) > 1 else self.flat.numel()
+        rc = L.lib().mot_dp_exchange_rows(h.multicast_ptr if self.algo == "nvls" else None,
+                                          h.buffer_ptrs_dev if self.algo == "p2p" else None, h.signal_pad_ptrs_dev,
+                                          self._work.data_ptr(), h.rank, h.world_size, self.offsets[0] * esz, V, D * esz,
+                                          self._bitmap_off, dense_lo * esz, (self.flat.numel() - dense_lo) * esz,
+                                          L.BF16 if self.dtype == torch.bfloat16 else L.F32, self._epoch,
+                                          L.DP_NVLS if self.algo == "nvls" else L.DP_P2P, stream)
+        L.check(rc, "mot_dp_exchange_rows")
+        self._epoch = (self._epoch + 2) & 0xFFFFFFFF
+        self._rows_ready = False
+
     def exchange_async(self, lo: int, hi: int, last: bool) -> None:
         """Average elements [lo, hi) of the bucket (multiples of 16 bytes) across ranks on the exchange stream, ordered
         after everything queued on the current stream (the backward of that slab).  Every rank issues the same calls;
@@ -222,7 +264,10 @@ class GradBucket:
                 return None
             dev = self.flat.device
             with torch.cuda.device(dev):
-                self._exchange(0, self.flat.numel(), True, torch.cuda.current_stream(dev).cuda_stream)
+                if self._rows_ready:       # the backward published its row bitmap: move only the rows of the union
+                    self._exchange_rows(torch.cuda.current_stream(dev).cuda_stream)
+                else:
+                    self._exchange(0, self.flat.numel(), True, torch.cuda.current_stream(dev).cuda_stream)
             return None
         if dist.get_backend(group) == "nccl":
             return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)

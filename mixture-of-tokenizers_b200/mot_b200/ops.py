@@ -496,6 +496,10 @@ class _MotEmbedFn(torch.autograd.Function):
                                plan_ready=planned, ws_clean=clean, stream=st, out_saved=out_saved, rstd=rstd,
                                plan_joined=planned)
         ws.clean = True           # every completed backward leaves the head of the workspace zeroed
+        if ctx.grad_bufs is not None and len(ctx.grad_bufs) > 2 and direct[0] is not None and tok is not None:
+            bk = ctx.grad_bufs[2]
+            if bk is not None and bk.sparse_rows and bk.params[0] is direct[0][0] and not bk._pending:
+                bk.mark_rows(desc, ws.buf)      # the rows this batch gathered: the exchange moves only the union
         ctx.ws = None
         release_workspace(ws)
         if g_lam is not None:
@@ -768,11 +772,15 @@ def mixout_split(x: torch.Tensor, bytes_per_token: int) -> torch.Tensor:
     return x.contiguous().view(*lead, T * bytes_per_token, D // bytes_per_token)
 
 
+_PROJ_KEEP_OPERAND = not __import__("os").environ.get("MOT_PROJ_REGATHER")
+
+
 class _MotEmbedProjFn(torch.autograd.Function):
     """out = f_out( [tok | bytes] . W^T + bias ): the fused gather builds the [n, K] operand (mot_embed_fwd, CONCAT),
     the projection runs on the tensor cores (mot_linear_fwd), the row norm after it is a separate HBM-bound pass over
     the bf16 product (the reference also rounds F.linear's output to bf16 before its rms_norm).  The [n, K] operand is
-    not kept for the backward: it is gathered again (0.1 ms against 0.7 ms of GEMMs, and n*K*2 bytes less to hold)."""
+    kept for the backward (n*K*2 bytes: 268 MB at 64K x 2048, small on 180 GB; saves one gather pass, ~0.1 ms of a 1.2 ms
+    step); MOT_PROJ_REGATHER=1 gathers it again instead (the round-1 behaviour, for memory-tight callers)."""
 
     @staticmethod
     def forward(ctx, spec: MixSpec, bpt: int, tokens, byte_ids, E_tok, E_byte, W, bias, byte_ids2=None):
@@ -826,7 +834,9 @@ class _MotEmbedProjFn(torch.autograd.Function):
             raise NotImplementedError("mot_b200: the projection bias must be fp32 (mathblations/model.py:261)")
         b32 = bias.detach().contiguous() if bias is not None else None
         linear_forward_out(A, w16, Y, b32)
-        del A
+        keep_A = _PROJ_KEEP_OPERAND and any(ctx.needs_input_grad[4:8])
+        if not keep_A:
+            del A
         if spec.out_norm:
             out = torch.empty_like(Y)
             rmsnorm_forward_out(Y, out, spec.eps)
@@ -836,12 +846,14 @@ class _MotEmbedProjFn(torch.autograd.Function):
         ctx.desc, ctx.dev, ctx.spec = desc, dev, spec
         ctx.w_dtype, ctx.has_bias = W.dtype, bias is not None
         ctx.pair, ctx.bpt, ctx.K = ids2 is not None, bpt, K
-        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y, ids2 if ids2 is not None else _ABSENT)
+        ctx.save_for_backward(tok, ids, E_tok_c, E_byte_c, w16, Y, ids2 if ids2 is not None else _ABSENT,
+                              A if keep_A else _ABSENT)
+        ctx.kept_A = keep_A
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        tok, ids, E_tok, E_byte, w16, Y, ids2 = ctx.saved_tensors
+        tok, ids, E_tok, E_byte, w16, Y, ids2, A_kept = ctx.saved_tensors
         desc, dev, spec = ctx.desc, ctx.dev, ctx.spec
         n, K, Do = tok.numel(), ctx.K, w16.shape[0]
         cdt = Y.dtype
@@ -852,16 +864,20 @@ class _MotEmbedProjFn(torch.autograd.Function):
         else:
             dY = g
         g_bias = colsum_out(dY) if ctx.has_bias else None
-        A = torch.empty((n, K), dtype=cdt, device=dev)
-        if not ctx.pair:
-            embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)   # gathered again, not kept
-        elif n > 0:
-            embed_forward_out(desc, tok, None, None, E_tok, None, None, A)
-            byte_pair_forward_out(ids, ids2, ctx.bpt, E_byte, A, E_tok.shape[1], spec.eps)
+        if ctx.kept_A:
+            A = A_kept                                                        # the forward's operand (n*K elements held)
+            dA = torch.empty((n, K), dtype=cdt, device=dev)                   # a saved tensor is never overwritten
+        else:
+            A = torch.empty((n, K), dtype=cdt, device=dev)
+            if not ctx.pair:
+                embed_forward_out(desc, tok, ids, None, E_tok, E_byte, None, A)   # gathered again (MOT_PROJ_REGATHER=1)
+            elif n > 0:
+                embed_forward_out(desc, tok, None, None, E_tok, None, None, A)
+                byte_pair_forward_out(ids, ids2, ctx.bpt, E_byte, A, E_tok.shape[1], spec.eps)
+            dA = A                                                            # dX may overwrite the private copy
         dW32 = torch.empty((Do, K), dtype=torch.float32, device=dev)
         dW16 = torch.empty((Do, K), dtype=torch.bfloat16, device=dev) if ctx.w_dtype == torch.bfloat16 else None
         linear_bwd_weight_out(dY, A, dW32, dW16)
-        dA = A                                                                # reuse the buffer
         linear_bwd_input_out(dY, w16, dA)
         gE_tok, gE_byte = torch.empty_like(E_tok), torch.empty_like(E_byte)
         ws, planned = ctx.ws, ctx.ws is not None

@@ -103,6 +103,13 @@ def _worker(rank, world, port, q):
                 bucket.all_reduce_avg()
             torch.cuda.synchronize()
             res[n_slabs] = (m.embed_tokens.weight.grad.clone(), m.embed_bytes.weight.grad.clone())
+            if n_slabs == 1:
+                assert bucket.sparse_rows, "the touched-rows exchange should be available here"
+                seen = torch.zeros(V, dtype=torch.int32, device=dev)
+                seen[tok.long()] = 1
+                dist.all_reduce(seen, op=dist.ReduceOp.MAX)
+                nobody = seen == 0                      # rows no rank gathered: exactly zero, never exchanged
+                assert bool(nobody.any()) and float(res[1][0][nobody].abs().max()) == 0.0
             if n_slabs == 1:   # fp32 reference: average of the ranks' own (un-exchanged) gradients
                 m2 = mot_b200.MoTEmbedding(V, 458, Dt, bd, bpt, variant="V3").to(dev).bfloat16()
                 m2.load_state_dict(m.state_dict())
