@@ -548,10 +548,9 @@ def run_ours(args):
         dist.all_reduce(errt, op=dist.ReduceOp.MAX)
         union_density = None
         if bucket.sparse_rows:
-            bm = bucket.bitmap.clone()
-            dist.all_reduce(bm, op=dist.ReduceOp.BOR)
-            bits = bm.view(torch.uint8)
-            union_density = float(sum(int(((bits >> k) & 1).sum()) for k in range(8))) / V_TOK
+            rows_hit = ((bucket.bitmap[:, None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(-1)[:V_TOK].contiguous()
+            dist.all_reduce(rows_hit, op=dist.ReduceOp.MAX)        # NCCL has no bitwise OR: one int per row
+            union_density = float(rows_hit.float().mean())
         dp_info = {"exchange": bucket.algo + (" (touched rows only)" if bucket.sparse_rows else ""), "rows_union_density": union_density,
                    "n_slabs": n_slabs, "reserve_sms": bucket.reserve_sms if n_slabs > 1 else 0,
                    "allreduce_ms": ar_ms, "touched_rows_allreduce_ms": ar_rows_ms, "nccl_allreduce_ms": nccl_ms, "compute_only_ms": comp_ms,

@@ -225,10 +225,11 @@ static void launch_p2p(int unroll, dim3 g, dim3 b, cudaStream_t s, char* const* 
 // real text touches 20-30 % per rank.  Work unit: 64 rows (two bitmap words), handed out by the tile counter; a warp owns a
 // row, its lanes the row's 16-byte vectors.
 constexpr int kRowsPerTile = 64;
-constexpr int kMaxVecPerLane = 4;   // rows up to 32 x 4 x 16 = 2048 bytes in one trip; wider rows loop
+constexpr int kMaxVecPerLane = 4;
+constexpr int kMaxRowWords = 2048; // bitmap words of one rank's rows held in shared memory (65536 rows per rank)   // rows up to 32 x 4 x 16 = 2048 bytes in one trip; wider rows loop
 
 template <bool BF16, bool NVLS, int WORLD>
-__global__ void __launch_bounds__(1024) rows_allreduce_avg_kernel(char* mc, char* const* peers, uint32_t* const* pads, int rank, int world,
+__global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(char* mc, char* const* peers, uint32_t* const* pads, int rank, int world,
                                                                  long long tab_off, int n_rows, int row_vecs, long long bm_off,
                                                                  long long dense_vec_lo, long long dense_vecs, uint32_t epoch,
                                                                  unsigned* work, long long* trace) {
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(1024) rows_allreduce_avg_kernel(char* mc, char
   const int r_lo = min(per * rank, n_rows), r_hi = min(r_lo + per, n_rows);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __shared__ long long tile_s[2];
-  __shared__ uint32_t bits_s[2][kRowsPerTile / 32];
+  __shared__ uint32_t bits_all[kMaxRowWords];   // union bitmap of this rank's rows, fetched once (one fabric round trip)
   auto or_word = [&](int w) -> uint32_t {  // union over the ranks of bitmap word w
     uint32_t v = 0;
     if (NVLS) {
@@ -267,74 +268,98 @@ __global__ void __launch_bounds__(1024) rows_allreduce_avg_kernel(char* mc, char
     return v;
   };
   if (threadIdx.x == 0) tile_s[0] = (long long)atomicAdd(work, 1u);
+  for (int w = threadIdx.x; w < (r_hi - r_lo + 31) / 32; w += blockDim.x) bits_all[w] = or_word((r_lo >> 5) + w);
   __syncthreads();
   for (int it = 0;; ++it) {
     const long long row0 = (long long)r_lo + tile_s[it & 1] * kRowsPerTile;
     if (row0 >= r_hi) break;
     if (threadIdx.x == 0) tile_s[(it + 1) & 1] = (long long)atomicAdd(work, 1u);
-    if (threadIdx.x < kRowsPerTile / 32) bits_s[it & 1][threadIdx.x] = or_word((int)(row0 >> 5) + threadIdx.x);
-    __syncthreads();
-    for (int rr = warp; rr < kRowsPerTile; rr += nw) {
-      const long long row = row0 + rr;
-      if (row >= r_hi) break;
-      if (!((bits_s[it & 1][rr >> 5] >> (rr & 31)) & 1u)) continue;   // zero on every rank: nothing to move
-      const long long v0 = tab_off / 16 + row * row_vecs;
+    const uint32_t* bits_t = bits_all + ((row0 - r_lo) >> 5);
+    // a warp owns rows warp, warp + nw, ... of the tile; RPW of them are in flight together: every load of those rows is
+    // issued before the first value is used (an NVLink round trip is ~2 us; with one row at a time the peer-to-peer
+    // version ran at 250 GB/s)
+    constexpr int RPW = NVLS ? 2 : (WORLD <= 2 ? 2 : 1);
+    for (int rr0 = warp; rr0 < kRowsPerTile; rr0 += nw * RPW) {
+      long long vrow[RPW];
+      bool act[RPW];
+#pragma unroll
+      for (int q2 = 0; q2 < RPW; ++q2) {
+        const int rr = rr0 + q2 * nw;
+        const long long row = row0 + rr;
+        act[q2] = rr < kRowsPerTile && row < r_hi && ((bits_t[rr >> 5] >> (rr & 31)) & 1u);
+        vrow[q2] = tab_off / 16 + row * row_vecs;
+      }
       for (int j0 = 0; j0 < row_vecs; j0 += 32 * kMaxVecPerLane) {
-        uint32_t r[kMaxVecPerLane][4];
         if (NVLS) {
+          uint32_t r[RPW][kMaxVecPerLane][4];
 #pragma unroll
-          for (int u = 0; u < kMaxVecPerLane; ++u) {
-            const int j = j0 + u * 32 + lane;
-            if (j < row_vecs) {
-              char* a = mc + (v0 + j) * 16;
-              if (BF16)
-                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(r[u][0]), "=r"(r[u][1]), "=r"(r[u][2]), "=r"(r[u][3]) : "l"(a) : "memory");
-              else
-                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(r[u][0]), "=r"(r[u][1]), "=r"(r[u][2]), "=r"(r[u][3]) : "l"(a) : "memory");
-            }
-          }
+          for (int q2 = 0; q2 < RPW; ++q2)
 #pragma unroll
-          for (int u = 0; u < kMaxVecPerLane; ++u) {
-            const int j = j0 + u * 32 + lane;
-            if (j < row_vecs) {
-              scale_vec(r[u], inv, BF16);
-              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + (v0 + j) * 16), "r"(r[u][0]),
-                           "r"(r[u][1]), "r"(r[u][2]), "r"(r[u][3]) : "memory");
-            }
-          }
-        } else {
-#pragma unroll 2
-          for (int u = 0; u < kMaxVecPerLane; ++u) {
-            const int j = j0 + u * 32 + lane;
-            if (j < row_vecs) {
-              uint32_t v[WORLD][4];
-#pragma unroll
-              for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + (v0 + j) * 16, v[q]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (BF16) {
-                  float a = 0.f, b = 0.f;
-#pragma unroll
-                  for (int q = 0; q < WORLD; ++q) {
-                    float lo_f, hi_f;
-                    bf16x2_to_f32(v[q][k], lo_f, hi_f);
-                    a += lo_f;
-                    b += hi_f;
-                  }
-                  r[u][k] = f32x2_to_bf16x2(a * inv, b * inv);
-                } else {
-                  float a = 0.f;
-#pragma unroll
-                  for (int q = 0; q < WORLD; ++q) a += __uint_as_float(v[q][k]);
-                  r[u][k] = __float_as_uint(a * inv);
-                }
+            for (int u = 0; u < kMaxVecPerLane; ++u) {
+              const int j = j0 + u * 32 + lane;
+              if (act[q2] && j < row_vecs) {
+                char* a = mc + (vrow[q2] + j) * 16;
+                if (BF16)
+                  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                               : "=r"(r[q2][u][0]), "=r"(r[q2][u][1]), "=r"(r[q2][u][2]), "=r"(r[q2][u][3]) : "l"(a) : "memory");
+                else
+                  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                               : "=r"(r[q2][u][0]), "=r"(r[q2][u][1]), "=r"(r[q2][u][2]), "=r"(r[q2][u][3]) : "l"(a) : "memory");
               }
-#pragma unroll
-              for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + (v0 + j) * 16, r[u]);
             }
-          }
+#pragma unroll
+          for (int q2 = 0; q2 < RPW; ++q2)
+#pragma unroll
+            for (int u = 0; u < kMaxVecPerLane; ++u) {
+              const int j = j0 + u * 32 + lane;
+              if (act[q2] && j < row_vecs) {
+                scale_vec(r[q2][u], inv, BF16);
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + (vrow[q2] + j) * 16),
+                             "r"(r[q2][u][0]), "r"(r[q2][u][1]), "r"(r[q2][u][2]), "r"(r[q2][u][3]) : "memory");
+              }
+            }
+        } else {
+          uint32_t v[RPW][kMaxVecPerLane][WORLD][4];
+#pragma unroll
+          for (int q2 = 0; q2 < RPW; ++q2)
+#pragma unroll
+            for (int u = 0; u < kMaxVecPerLane; ++u) {
+              const int j = j0 + u * 32 + lane;
+              if (act[q2] && j < row_vecs) {
+#pragma unroll
+                for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + (vrow[q2] + j) * 16, v[q2][u][q]);
+              }
+            }
+#pragma unroll
+          for (int q2 = 0; q2 < RPW; ++q2)
+#pragma unroll
+            for (int u = 0; u < kMaxVecPerLane; ++u) {
+              const int j = j0 + u * 32 + lane;
+              if (act[q2] && j < row_vecs) {
+                uint32_t r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (BF16) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int q = 0; q < WORLD; ++q) {
+                      float lo_f, hi_f;
+                      bf16x2_to_f32(v[q2][u][q][k], lo_f, hi_f);
+                      a += lo_f;
+                      b += hi_f;
+                    }
+                    r[k] = f32x2_to_bf16x2(a * inv, b * inv);
+                  } else {
+                    float a = 0.f;
+#pragma unroll
+                    for (int q = 0; q < WORLD; ++q) a += __uint_as_float(v[q2][u][q][k]);
+                    r[k] = __float_as_uint(a * inv);
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < WORLD; ++q) st_sys_16(P[q] + (vrow[q2] + j) * 16, r);
+              }
+            }
         }
       }
     }
@@ -480,12 +505,13 @@ extern "C" int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_
   if (algo != MOT_DP_NVLS && algo != MOT_DP_P2P) return MOT_ERR_UNSUPPORTED;
   if (algo == MOT_DP_P2P && world != 2 && world != 4) return MOT_ERR_UNSUPPORTED;
   if (world > 16) return MOT_ERR_UNSUPPORTED;
+  if (((n_rows + world - 1) / world + 31) / 32 + 1 > kMaxRowWords) return MOT_ERR_UNSUPPORTED;
   if ((row_bytes & 15) || (table_byte_offset & 15) || (bitmap_byte_offset & 3) || (dense_byte_offset & 15) || (dense_bytes & 15))
     return MOT_ERR_MISALIGNED;
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   const char* env_b = getenv("MOT_AR_BLOCKS");
-  long long blocks = env_b ? atoi(env_b) : (algo == MOT_DP_NVLS ? kArMaxBlocksNvls : 16);
+  long long blocks = env_b ? atoi(env_b) : (algo == MOT_DP_NVLS ? kArMaxBlocksNvls : kArMaxBlocksP2p);
   if (blocks < 1) blocks = 1;
   if (blocks * world > kPadSlots) blocks = kPadSlots / world;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -495,7 +521,7 @@ extern "C" int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_
   long long* trace = g_trace ? g_trace + (3 * 4096 + (size_t)(trace_seq++ % 16) * 64) * 64 : nullptr;
   char* mc = reinterpret_cast<char*>(multicast_ptr);
   char* const* peers = reinterpret_cast<char* const*>(peer_ptrs_dev);
-  const dim3 g((unsigned)blocks), b(1024);
+  const dim3 g((unsigned)blocks), b(algo == MOT_DP_NVLS ? 1024 : 512);
   const int row_vecs = row_bytes / 16;
   const long long dlo = dense_byte_offset / 16, dn = dense_bytes / 16;
   const bool bf = dtype == MOT_BF16;
