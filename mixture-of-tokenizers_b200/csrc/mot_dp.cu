@@ -232,7 +232,7 @@ template <bool BF16, bool NVLS, int WORLD>
 __global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(char* mc, char* const* peers, uint32_t* const* pads, int rank, int world,
                                                                  long long tab_off, int n_rows, int row_vecs, long long bm_off,
                                                                  long long dense_vec_lo, long long dense_vecs, uint32_t epoch,
-                                                                 unsigned* work, long long* trace) {
+                                                                 unsigned* work, int peer_bits, long long* trace) {
   pdl_launch_dependents();
   MOT_STAMP(trace, blockIdx.x, 0);
   pdl_wait();
@@ -253,7 +253,11 @@ __global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __shared__ long long tile_s[2];
   __shared__ uint32_t bits_all[kMaxRowWords];   // union bitmap of this rank's rows, fetched once (one fabric round trip)
-  auto or_word = [&](int w) -> uint32_t {  // union over the ranks of bitmap word w
+  // peer-to-peer: the bitmap of every rank as well.  A row a rank did not gather is a row of zeros in that rank's copy (the
+  // dense-gradient contract of the backward), so it is not read at all: the pull phase moves the rows each PEER gathered
+  // (62 % of the table per rank for uniform ids at 48K tokens), the push phase the rows of the union (86 % at 2 ranks).
+  __shared__ uint32_t bits_rank[NVLS ? 1 : WORLD][NVLS ? 1 : kMaxRowWords];
+  auto or_word = [&](int w_local, int w) -> uint32_t {  // union over the ranks of bitmap word w
     uint32_t v = 0;
     if (NVLS) {
       asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b32 %0, [%1];" : "=r"(v) : "l"(mc + bm_off + (long long)w * 4) : "memory");
@@ -262,13 +266,14 @@ __global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(c
       for (int q = 0; q < WORLD; ++q) {
         uint32_t x;
         asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(x) : "l"(P[q] + bm_off + (long long)w * 4) : "memory");
+        bits_rank[q][w_local] = peer_bits ? x : 0xffffffffu;
         v |= x;
       }
     }
     return v;
   };
   if (threadIdx.x == 0) tile_s[0] = (long long)atomicAdd(work, 1u);
-  for (int w = threadIdx.x; w < (r_hi - r_lo + 31) / 32; w += blockDim.x) bits_all[w] = or_word((r_lo >> 5) + w);
+  for (int w = threadIdx.x; w < (r_hi - r_lo + 31) / 32; w += blockDim.x) bits_all[w] = or_word(w, (r_lo >> 5) + w);
   __syncthreads();
   for (int it = 0;; ++it) {
     const long long row0 = (long long)r_lo + tile_s[it & 1] * kRowsPerTile;
@@ -282,12 +287,19 @@ __global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(c
     for (int rr0 = warp; rr0 < kRowsPerTile; rr0 += nw * RPW) {
       long long vrow[RPW];
       bool act[RPW];
+      uint32_t has[RPW];  // peer-to-peer: bit q = rank q gathered the row (its copy is read), else its copy is zeros
 #pragma unroll
       for (int q2 = 0; q2 < RPW; ++q2) {
         const int rr = rr0 + q2 * nw;
         const long long row = row0 + rr;
         act[q2] = rr < kRowsPerTile && row < r_hi && ((bits_t[rr >> 5] >> (rr & 31)) & 1u);
         vrow[q2] = tab_off / 16 + row * row_vecs;
+        has[q2] = 0u;
+        if (!NVLS && act[q2]) {
+          const int wl = (int)((row0 - r_lo) >> 5) + (rr >> 5);
+#pragma unroll
+          for (int q = 0; q < WORLD; ++q) has[q2] |= ((bits_rank[q][wl] >> (rr & 31)) & 1u) << q;
+        }
       }
       for (int j0 = 0; j0 < row_vecs; j0 += 32 * kMaxVecPerLane) {
         if (NVLS) {
@@ -327,7 +339,13 @@ __global__ void __launch_bounds__(NVLS ? 1024 : 512) rows_allreduce_avg_kernel(c
               const int j = j0 + u * 32 + lane;
               if (act[q2] && j < row_vecs) {
 #pragma unroll
-                for (int q = 0; q < WORLD; ++q) ld_sys_16(P[q] + (vrow[q2] + j) * 16, v[q2][u][q]);
+                for (int q = 0; q < WORLD; ++q) {
+                  if ((has[q2] >> q) & 1u) {
+                    ld_sys_16(P[q] + (vrow[q2] + j) * 16, v[q2][u][q]);
+                  } else {
+                    v[q2][u][q][0] = v[q2][u][q][1] = v[q2][u][q][2] = v[q2][u][q][3] = 0u;  // +0.0 in bf16x2 and fp32 alike
+                  }
+                }
               }
             }
 #pragma unroll
@@ -511,6 +529,8 @@ extern "C" int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_
   int sms = 0, optin = 0;
   if (int rc = device_props(&sms, &optin)) return rc;
   const char* env_b = getenv("MOT_AR_BLOCKS");
+  const char* env_pb = getenv("MOT_DP_PEER_BITS");   // debug knob: 0 = read every copy of a union row (round-2 behaviour)
+  const int peer_bits = env_pb ? atoi(env_pb) : 1;
   long long blocks = env_b ? atoi(env_b) : (algo == MOT_DP_NVLS ? kArMaxBlocksNvls : kArMaxBlocksP2p);
   if (blocks < 1) blocks = 1;
   if (blocks * world > kPadSlots) blocks = kPadSlots / world;
@@ -527,7 +547,7 @@ extern "C" int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_
   const bool bf = dtype == MOT_BF16;
 #define MOT_ROWS_LAUNCH(BF, NV, WD)                                                                                         \
   launch_pdl(rows_allreduce_avg_kernel<BF, NV, WD>, g, b, 0, s, mc, peers, pads, (int)rank, (int)world, (long long)table_byte_offset, \
-             (int)n_rows, row_vecs, (long long)bitmap_byte_offset, dlo, dn, epoch, work, trace)
+             (int)n_rows, row_vecs, (long long)bitmap_byte_offset, dlo, dn, epoch, work, peer_bits, trace)
   if (algo == MOT_DP_NVLS) {
     if (bf) MOT_ROWS_LAUNCH(true, true, 1); else MOT_ROWS_LAUNCH(false, true, 1);
   } else if (world == 2) {

@@ -24,6 +24,14 @@ namespace mot {
 #ifndef MOT_SUM_TWO_PASS
 #define MOT_SUM_TWO_PASS 0
 #endif
+// Byte gradients through the TMA engine: the warp writes dz (fp32) over the ring stage it has just consumed and the lanes
+// that hold the byte ids each hand one slot (bd floats) to cp.reduce.async.bulk...add.f32, which adds it into the L2-resident
+// accumulator replica.  The SM issues bpt bulk operations per occurrence instead of 32 x CPL RED.128, no id shuffles, and
+// the reductions drain beside the next occurrence; the stage is refilled one occurrence later (when the bulk group has
+// read it).  Measurements: profiles/r2_experiments.md.
+#ifndef MOT_SUM_BULK_RED
+#define MOT_SUM_BULK_RED 0
+#endif
 constexpr int kSumThreads = MOT_SUM_THREADS;
 
 struct SumSmem {
@@ -197,6 +205,7 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   MOT_STAMP(p.trace, gw, 3);
 
   // ---- per-lane constants: byte slot and accumulator offset of each of the lane's chunks ----
+#if !MOT_SUM_BULK_RED || MOT_SUM_TWO_PASS
   int slot[CPL];
   unsigned boff4[CPL];  // byte offset of the lane's chunk inside a row of the fp32 accumulator
 #pragma unroll
@@ -206,6 +215,9 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
     boff4[it] = (unsigned)(e - slot[it] * p.bd) * 4u;
     asm volatile("" : "+r"(slot[it]), "+r"(boff4[it]));  // keep them in registers (no 64-bit rematerialisation per use)
   }
+#else
+  bool red_pending = false;  // the previous occurrence's stage still feeds its bulk reductions (released one occurrence later)
+#endif
   const unsigned bd4 = (unsigned)p.bd * 4u;
   char* accp = reinterpret_cast<char*>(p.byte_acc + (size_t)(gw % p.n_rep) * p.Vb * p.bd);
   const float inv_Do = 1.f / (float)p.Do;
@@ -279,6 +291,10 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
 #endif
       const T* grow = reinterpret_cast<const T*>(ring + (size_t)cs * stage_bytes);
       const T* orow = reinterpret_cast<const T*>(ring + (size_t)cs * stage_bytes + row_off);
+#if MOT_SUM_BULK_RED
+      float* dzrow = reinterpret_cast<float*>(ring + (size_t)cs * stage_bytes);  // dz (fp32) overwrites [g | o] in place
+      const uint32_t dz_s = ring_s + (uint32_t)cs * stage_bytes;
+#endif
       if (++cs == D) {
         cs = 0;
         cpar ^= 1u;
@@ -327,24 +343,54 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
       }
       float gz = (gzp[0] + gzp[1]) + (gzp[2] + gzp[3]);
       gz = warp_sum(gz);  // every lane has its shared-memory reads in registers here: the stage can be refilled
+#if !MOT_SUM_BULK_RED
       --inflight;
       try_issue();
+#endif
       const float c = r * gz * inv_Do;
 #ifdef MOT_X_SUM_NO_MATH
       if (c == 12345.678f)
 #endif
 #pragma unroll
       for (int it = 0; it < CPL; ++it) {
+#if !MOT_SUM_BULK_RED
         const int id = __shfl_sync(kFull, idreg, slot[it]);
+#endif
         float dz[CW];
 #pragma unroll
         for (int e = 0; e < CW; ++e) {
           dz[e] = r * g[it][e] - c * o[it][e];
           Du[it][e] += dz[e];
         }
+#if MOT_SUM_BULK_RED
+        *reinterpret_cast<float4*>(dzrow + (it * 32 + lane) * CW) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+#else
         MOT_ASSERT(id >= 0 && id < p.Vb, "byte id", id, p.Vb);
         gmem_add4(reinterpret_cast<float*>(accp + ((unsigned)id * bd4 + boff4[it])), dz);
+#endif
       }
+#if MOT_SUM_BULK_RED
+      // generic-proxy writes of dz -> visible to the async proxy, then one bulk reduction per byte slot (lane = slot)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (id_lane) {
+        MOT_ASSERT(idreg >= 0 && idreg < p.Vb, "byte id", idreg, p.Vb);
+#ifndef MOT_EXPERIMENT_NO_RED
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(accp + (unsigned)idreg * bd4),
+                     "r"(dz_s + (unsigned)lane * bd4), "r"(bd4)
+                     : "memory");
+#endif
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // every group but the one just committed has finished READING its stage: the previous occurrence's stage is free
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+      __syncwarp();
+      if (red_pending) {
+        --inflight;
+        try_issue();
+      }
+      red_pending = true;
+#endif
 #endif
     }
     if (A.flags & 2) {  // end of the chunk: close the open row segment
@@ -395,6 +441,10 @@ __global__ void __launch_bounds__(kSumThreads, 1) mot_bwd_sum_kernel(const Embed
   }
 #endif
   MOT_STAMP(p.trace, gw, 62);
+#if MOT_SUM_BULK_RED && !MOT_SUM_TWO_PASS
+  // the bulk reductions drained beside the zero fill; they must be complete (and the ring intact) when the thread exits
+  if (id_lane) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 #ifdef MOT_TRACE
   if (p.trace != nullptr && lane == 0) p.trace[(size_t)gw * 64 + 63] = n_occ;
 #endif

@@ -81,45 +81,51 @@ def _worker(rank, world, port, q):
                 dist.broadcast(other, src=0)
                 assert torch.equal(mine, other), (algo, dtype, "ranks disagree")
             notes.append(algo)
-        # ---- the pipelined step of the MoT-sum module against the one-piece step ----
-        os.environ["MOT_DP_ALGO"] = algos[-1]
-        V, Dt, bd, bpt, N = 50257, 256, 16, 16, 20000
-        res = {}
-        for n_slabs in (1, 4):
-            torch.manual_seed(0)
-            m = mot_b200.MoTEmbedding(V, 458, Dt, bd, bpt, variant="V3").to(dev).bfloat16()
-            dp.broadcast_params(m.parameters())
-            bucket = m.attach_grad_bucket(dp.GradBucket([m.embed_tokens.weight, m.embed_bytes.weight], symmetric=True,
-                                                        n_slabs=n_slabs))
-            assert bucket.pipelined == (n_slabs > 1)
-            g = torch.Generator(device=dev).manual_seed(7 + rank)        # every rank its own shard of the batch
-            tok = torch.randint(0, V, (N,), generator=g, device=dev, dtype=torch.int32)
-            ids = torch.randint(0, 458, (bpt, N), generator=g, device=dev, dtype=torch.int32)
-            go = torch.randn(1, N, Dt, generator=g, device=dev).bfloat16()
-            for step in range(2):
-                for p_ in m.parameters():
-                    p_.grad = None
-                m(tok, ids).backward(go)
-                bucket.all_reduce_avg()
-            torch.cuda.synchronize()
-            res[n_slabs] = (m.embed_tokens.weight.grad.clone(), m.embed_bytes.weight.grad.clone())
-            if n_slabs == 1:
-                assert bucket.sparse_rows, "the touched-rows exchange should be available here"
-                seen = torch.zeros(V, dtype=torch.int32, device=dev)
-                seen[tok.long()] = 1
-                dist.all_reduce(seen, op=dist.ReduceOp.MAX)
-                nobody = seen == 0                      # rows no rank gathered: exactly zero, never exchanged
-                assert bool(nobody.any()) and float(res[1][0][nobody].abs().max()) == 0.0
-            if n_slabs == 1:   # fp32 reference: average of the ranks' own (un-exchanged) gradients
-                m2 = mot_b200.MoTEmbedding(V, 458, Dt, bd, bpt, variant="V3").to(dev).bfloat16()
-                m2.load_state_dict(m.state_dict())
-                m2(tok, ids).backward(go)
-                want = [m2.embed_tokens.weight.grad.float(), m2.embed_bytes.weight.grad.float()]
-                for w in want:
-                    dist.all_reduce(w, op=dist.ReduceOp.SUM)
-                    w /= world
-                assert _nerr(res[1][0], want[0]) <= 2.0 ** -7 and _nerr(res[1][1], want[1]) <= 2.0 ** -7
-        assert _nerr(res[4][0], res[1][0]) <= 2.0 ** -7 and _nerr(res[4][1], res[1][1]) <= 2.0 ** -7
+        # ---- the pipelined step of the MoT-sum module against the one-piece step, with every exchange the box offers
+        #      (peer-to-peer at 2 / 4 ranks moves only the rows each PEER gathered, NVLS the rows of the union) ----
+        for step_algo in algos:
+            os.environ["MOT_DP_ALGO"] = step_algo
+            V, Dt, bd, bpt, N = 50257, 256, 16, 16, 20000
+            res = {}
+            for n_slabs in (1, 4):
+                torch.manual_seed(0)
+                m = mot_b200.MoTEmbedding(V, 458, Dt, bd, bpt, variant="V3").to(dev).bfloat16()
+                dp.broadcast_params(m.parameters())
+                bucket = m.attach_grad_bucket(dp.GradBucket([m.embed_tokens.weight, m.embed_bytes.weight], symmetric=True,
+                                                            n_slabs=n_slabs))
+                assert bucket.pipelined == (n_slabs > 1)
+                g = torch.Generator(device=dev).manual_seed(7 + rank)        # every rank its own shard of the batch
+                tok = torch.randint(0, V, (N,), generator=g, device=dev, dtype=torch.int32)
+                ids = torch.randint(0, 458, (bpt, N), generator=g, device=dev, dtype=torch.int32)
+                go = torch.randn(1, N, Dt, generator=g, device=dev).bfloat16()
+                for step in range(2):
+                    for p_ in m.parameters():
+                        p_.grad = None
+                    m(tok, ids).backward(go)
+                    bucket.all_reduce_avg()
+                torch.cuda.synchronize()
+                res[n_slabs] = (m.embed_tokens.weight.grad.clone(), m.embed_bytes.weight.grad.clone())
+                if n_slabs == 1:
+                    assert bucket.sparse_rows == (step_algo == "nvls" or world in (2, 4)), "touched-rows exchange availability"
+                    seen = torch.zeros(V, dtype=torch.int32, device=dev)
+                    seen[tok.long()] = 1
+                    dist.all_reduce(seen, op=dist.ReduceOp.MAX)
+                    nobody = seen == 0                      # rows no rank gathered: exactly zero, never exchanged
+                    assert bool(nobody.any()) and float(res[1][0][nobody].abs().max()) == 0.0
+                    mine = res[1][0].clone().view(torch.uint8)       # every rank holds the same bits
+                    other = mine.clone()
+                    dist.broadcast(other, src=0)
+                    assert torch.equal(mine, other), (step_algo, "ranks disagree after the touched-rows exchange")
+                if n_slabs == 1:   # fp32 reference: average of the ranks' own (un-exchanged) gradients
+                    m2 = mot_b200.MoTEmbedding(V, 458, Dt, bd, bpt, variant="V3").to(dev).bfloat16()
+                    m2.load_state_dict(m.state_dict())
+                    m2(tok, ids).backward(go)
+                    want = [m2.embed_tokens.weight.grad.float(), m2.embed_bytes.weight.grad.float()]
+                    for w in want:
+                        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+                        w /= world
+                    assert _nerr(res[1][0], want[0]) <= 2.0 ** -7 and _nerr(res[1][1], want[1]) <= 2.0 ** -7
+            assert _nerr(res[4][0], res[1][0]) <= 2.0 ** -7 and _nerr(res[4][1], res[1][1]) <= 2.0 ** -7
         q.put((rank, "ok " + "+".join(notes)))
     except Exception as e:  # pragma: no cover
         import traceback
