@@ -93,3 +93,36 @@ def test_grad_bucket_single_process_layout():
     c.grad = torch.ones(4, 4)
     with pytest.raises(TypeError):
         bk2.attach()
+
+
+def test_pick_algo_policy_and_overrides(monkeypatch):
+    """Which exchange runs the bucket (mot_b200/dp.py:pick_algo; measured in profiles/r2_dp.md): peer-to-peer two-shot at 2
+    ranks, the in-switch reduction from 3 ranks where the switch offers multicast, peer-to-peer at 4 / 8 without it, NCCL
+    for everything else; MOT_DP_ALGO / MOT_DP_NCCL force one and never select an exchange the box cannot run."""
+    from mot_b200 import dp
+    for k in ("MOT_DP_ALGO", "MOT_DP_NCCL"):
+        monkeypatch.delenv(k, raising=False)
+    assert dp.pick_algo(2, True) == "p2p" and dp.pick_algo(2, False) == "p2p"
+    assert [dp.pick_algo(n, True) for n in (3, 4, 8, 16)] == ["nvls"] * 4
+    assert dp.pick_algo(4, False) == "p2p" and dp.pick_algo(8, False) == "p2p"
+    assert dp.pick_algo(3, False) == "nccl" and dp.pick_algo(6, False) == "nccl"
+    monkeypatch.setenv("MOT_DP_ALGO", "nvls")
+    assert dp.pick_algo(8, True) == "nvls" and dp.pick_algo(8, False) == "nccl"     # no multicast: NCCL, not a broken path
+    monkeypatch.setenv("MOT_DP_ALGO", "p2p")
+    assert dp.pick_algo(4, True) == "p2p" and dp.pick_algo(3, True) == "nccl"       # P2P kernels exist for 2 / 4 / 8 ranks
+    monkeypatch.setenv("MOT_DP_NCCL", "1")
+    assert dp.pick_algo(8, True) == "nccl"
+    assert dp.default_slabs(2) == 1 and dp.default_slabs(8) == 1                   # the slab pipeline is opt-in
+
+
+def test_grad_bucket_without_process_group_is_plain_memory():
+    """No initialised process group: the bucket is ordinary memory, the exchange a no-op, the pipeline refused."""
+    import torch
+    from mot_b200 import dp
+    ps = [torch.nn.Parameter(torch.zeros(10, 8)), torch.nn.Parameter(torch.zeros(3, 8))]
+    b = dp.GradBucket(ps, symmetric="auto")
+    assert b.algo == "nccl" and not b.pipelined and not b.sparse_rows and b.n_slabs == 1
+    assert b.all_reduce_avg() is None
+    with pytest.raises(RuntimeError):
+        b.exchange_async(0, 8, last=True)
+    b.wait()                                                                       # nothing pending: returns
