@@ -279,7 +279,10 @@ int mot_dp_exchange(void* multicast_ptr, void* const* peer_ptrs_dev, void* const
  * v; ceil(tok_vocab/32) uint32 words) -- call it after the backward, into the bucket's symmetric memory.
  * mot_dp_exchange_rows ORs the ranks' bitmaps through the fabric and averages only the rows of the union of the table at
  * [table_byte_offset, + n_rows*row_bytes), then the dense range [dense_byte_offset, + dense_bytes) (the byte table, other
- * parameters); both barriers: `epoch` grows by 2.  Rows that are zero everywhere stay untouched. */
+ * parameters); both barriers: `epoch` grows by 2.  Rows that are zero everywhere stay untouched.
+ * Precondition (the dense-gradient contract of mot_embed_bwd): a row whose bit is clear in a rank's bitmap is all zeros in
+ * that rank's copy -- the peer-to-peer variant does not read such a copy at all (MOT_DP_PEER_BITS=0 reads every copy of a
+ * union row, as the in-switch reduction necessarily does). */
 int mot_embed_touched_rows(const MotDesc* d, const void* workspace, size_t ws_bytes, uint32_t* bitmap, void* stream);
 int mot_dp_exchange_rows(void* multicast_ptr, void* const* peer_ptrs_dev, void* const* signal_pads_dev, void* work_area,
                          int32_t rank, int32_t world, int64_t table_byte_offset, int32_t n_rows, int32_t row_bytes,
