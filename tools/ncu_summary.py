@@ -19,6 +19,22 @@ for k in ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.s
           "sm__cycles_elapsed.max"]:
     v, u = get(k)
     print(f"  {k:62s} {v:>18s} {u}")
+print("memory paths (SM <-> crossbar <-> L2, L2 atomic units, inter-partition fabric):")
+for k in ["l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed",
+          "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+          "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed",
+          "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+          "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+          "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+          "lts__xbar2lts_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed",
+          "lts__d_sectors.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sectors_lookup_hit.sum",
+          "lts__t_sectors_lookup_miss.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+          "lts__t_sectors_srcunit_tex_op_red.avg.per_cycle_elapsed", "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum",
+          "lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum", "lts__t_sectors_srcunit_ltcfabric.sum",
+          "lts__t_sectors_srcunit_ltcfabric.avg.pct_of_peak_sustained_elapsed"]:
+    v, u = get(k)
+    if v != "n/a":
+        print(f"  {k:78s} {v:>18s} {u}")
 print("stall reasons (warps stalled per issue-active cycle):")
 st = [(k, float(r[i])) for i, k in enumerate(hdr) if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
 for k, v in sorted(st, key=lambda kv: -kv[1])[:8]:
